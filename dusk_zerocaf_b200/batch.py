@@ -1,0 +1,91 @@
+"""Batch API over host numpy arrays (uint64; FieldElement/Scalar = (n,5), points = (n,20)).
+
+Each function is one call through the C ABI with HOST buffers (copy in, kernel, copy out).  Names follow the
+reference's operators: field.rs / scalar.rs / edwards.rs / ristretto.rs Add, Sub, Mul, Neg, Square, Double.
+"""
+import numpy as np
+
+from .context import default_context
+
+
+def _arr(x, cols):
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    if x.ndim == 1:
+        x = x.reshape(1, -1)
+    if x.shape[-1] != cols:
+        raise ValueError(f"expected (..., {cols}) uint64 limbs, got {x.shape}")
+    return x
+
+
+def _bin(name, a, b, cols, ctx, out_cols=None):
+    ctx = ctx or default_context()
+    a, b = _arr(a, cols), _arr(b, cols)
+    if a.shape != b.shape:
+        raise ValueError("operand shapes differ")
+    out = np.empty((a.shape[0], out_cols or cols), dtype=np.uint64)
+    ctx.call(name, a, b, out, a.shape[0])
+    return out
+
+
+def _un(name, a, cols, ctx):
+    ctx = ctx or default_context()
+    a = _arr(a, cols)
+    out = np.empty_like(a)
+    ctx.call(name, a, out, a.shape[0])
+    return out
+
+
+def fe_mul(a, b, ctx=None): return _bin("zc_fe_mul_batch", a, b, 5, ctx)
+def fe_add(a, b, ctx=None): return _bin("zc_fe_add_batch", a, b, 5, ctx)
+def fe_sub(a, b, ctx=None): return _bin("zc_fe_sub_batch", a, b, 5, ctx)
+def fe_square(a, ctx=None): return _un("zc_fe_square_batch", a, 5, ctx)
+def fe_neg(a, ctx=None): return _un("zc_fe_neg_batch", a, 5, ctx)
+def scalar_mul(a, b, ctx=None): return _bin("zc_scalar_mul_batch", a, b, 5, ctx)
+def scalar_add(a, b, ctx=None): return _bin("zc_scalar_add_batch", a, b, 5, ctx)
+def scalar_sub(a, b, ctx=None): return _bin("zc_scalar_sub_batch", a, b, 5, ctx)
+def scalar_square(a, ctx=None): return _un("zc_scalar_square_batch", a, 5, ctx)
+def scalar_neg(a, ctx=None): return _un("zc_scalar_neg_batch", a, 5, ctx)
+def point_add(p, q, ctx=None): return _bin("zc_point_add_batch", p, q, 20, ctx)
+def point_sub(p, q, ctx=None): return _bin("zc_point_sub_batch", p, q, 20, ctx)
+def point_double(p, ctx=None): return _un("zc_point_double_batch", p, 20, ctx)
+def point_neg(p, ctx=None): return _un("zc_point_neg_batch", p, 20, ctx)
+
+
+def fe_mul_square(a, b, ctx=None):
+    ctx = ctx or default_context()
+    a, b = _arr(a, 5), _arr(b, 5)
+    prod, sq = np.empty_like(a), np.empty_like(a)
+    ctx.call("zc_fe_mul_square_batch", a, b, prod, sq, a.shape[0])
+    return prod, sq
+
+
+def point_scalar_mul(points, scalars, mode=0, ctx=None):
+    ctx = ctx or default_context()
+    p, s = _arr(points, 20), _arr(scalars, 5)
+    if p.shape[0] != s.shape[0]:
+        raise ValueError("points / scalars length differ")
+    out = np.empty_like(p)
+    ctx.call("zc_point_scalar_mul_batch", p, s, out, p.shape[0], int(mode))
+    return out
+
+
+def ristretto_eq(p, q, ctx=None):
+    ctx = ctx or default_context()
+    p, q = _arr(p, 20), _arr(q, 20)
+    out = np.empty(p.shape[0], dtype=np.uint8)
+    ctx.call("zc_ristretto_eq_batch", p, q, out, p.shape[0])
+    return out
+
+
+def msm(points, scalars, window_bits=16, ctx=None):
+    """sum_i [s_i] P_i as an EdwardsPoint (20 limbs); a group element, compare canonically."""
+    ctx = ctx or default_context()
+    out = np.empty(20, dtype=np.uint64)
+    if points is None or len(points) == 0:
+        ctx.check(ctx._L.zc_msm(ctx._h, None, None, 0, int(window_bits), out.ctypes.data))
+        return out
+    p, s = _arr(points, 20), _arr(scalars, 5)
+    if p.shape[0] != s.shape[0]:
+        raise ValueError("points / scalars length differ")
+    ctx.check(ctx._L.zc_msm(ctx._h, p.ctypes.data, s.ctypes.data, p.shape[0], int(window_bits), out.ctypes.data))
+    return out

@@ -1,0 +1,61 @@
+// zc_internal.h -- context object and launch helpers shared by the translation units of libzerocaf_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/zerocaf_b200.h"
+
+struct zc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t launches = 0;
+  char err[512] = {0};
+  // grow-only device scratch for the host-pointer entry points (three inputs/outputs + MSM workspace)
+  void *scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
+  // MSM workspace (device)
+  void *msm_ws = nullptr;
+  size_t msm_ws_bytes = 0;
+  // NCCL (resolved with dlopen, see zc_nccl.cu)
+  void *nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  void *gather_buf = nullptr;   // nranks * 20 u64, device
+};
+
+#define ZC_CUDA(ctx, call)                                                                       \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s", __FILE__, __LINE__, #call,      \
+               cudaGetErrorString(e__));                                                         \
+      return -(int32_t)e__;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+static inline int32_t zc_fail(zc_ctx *ctx, int32_t code, const char *msg) {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+  return code;
+}
+
+// grow-only scratch slot
+static inline int32_t zc_scratch(zc_ctx *ctx, int slot, size_t bytes, void **out) {
+  if (bytes > ctx->scratch_bytes[slot]) {
+    if (ctx->scratch[slot]) ZC_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    ZC_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], want));
+    ctx->scratch_bytes[slot] = want;
+  }
+  *out = ctx->scratch[slot];
+  return ZC_OK;
+}
+
+// implemented in zc_msm.cu
+int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits,
+                   int32_t rank, int32_t nranks, bool exchange, uint64_t *out_point_dev);

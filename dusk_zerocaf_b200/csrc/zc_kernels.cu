@@ -1,0 +1,484 @@
+// zc_kernels.cu -- batched field / scalar / point kernels and their C-ABI entry points (include/zerocaf_b200.h).
+//
+// One residue (or one point) per thread; operands stream through HBM in the reference's own AoS radix-2^52 layout and
+// are repacked to 8 x u32 Montgomery words in registers (zc_fe.cuh).  Every kernel is memory-streaming or
+// integer-multiply bound; none uses tensor cores (there is no dense contraction on this path).
+#include "zc_internal.h"
+#include "zc_point.cuh"
+
+using namespace zc;
+
+namespace {
+
+constexpr int TPB = 256;
+
+enum FeOp { OP_MUL = 0, OP_SQUARE = 1, OP_ADD = 2, OP_SUB = 3, OP_NEG = 4 };
+
+// ---- K1: out[i] = a[i] (op) b[i]   (field.rs:191-315 / scalar.rs:184-283) -------------------------------
+// Normal-form operands: a*b = mont(mont(a, R^2), b) -- two Montgomery products, no final fix-up multiply.
+template <class M, int OP>
+__global__ void __launch_bounds__(TPB) fe_op_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
+                                                    uint64_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  Fe x = fe_load52(a + 5 * i);
+  Fe r;
+  if (OP == OP_MUL) {
+    Fe y = fe_load52(b + 5 * i);
+    r = mont_mul<M>(to_mont<M>(x), y);
+  } else if (OP == OP_SQUARE) {
+    r = mont_mul<M>(to_mont<M>(x), x);
+  } else if (OP == OP_ADD) {
+    Fe y = fe_load52(b + 5 * i);
+    r = fe_add<M>(x, y);
+  } else if (OP == OP_SUB) {
+    Fe y = fe_load52(b + 5 * i);
+    r = fe_sub<M>(x, y);
+  } else {
+    r = fe_neg<M>(x);
+  }
+  fe_store52(out + 5 * i, r);
+}
+
+// ---- K1 fused (BASELINE config 2): prod = a*b, sq = a^2 sharing mont(a, R^2): 3 Montgomery products for 2 field ops
+template <class M>
+__global__ void __launch_bounds__(TPB) fe_mul_square_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
+                                                            uint64_t* __restrict__ prod, uint64_t* __restrict__ sq, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  Fe x = fe_load52(a + 5 * i);
+  Fe y = fe_load52(b + 5 * i);
+  Fe xm = to_mont<M>(x);
+  fe_store52(prod + 5 * i, mont_mul<M>(xm, y));
+  fe_store52(sq + 5 * i, mont_mul<M>(xm, x));
+}
+
+// ---- K2: point add / sub / double / neg on the ABI layout, limb-exact (edwards.rs:440-592) ----------------
+enum PtOp { PT_ADD = 0, PT_SUB = 1, PT_DOUBLE = 2, PT_NEG = 3 };
+
+template <int OP>
+__global__ void __launch_bounds__(TPB) pt_op_kernel(const uint64_t* __restrict__ p, const uint64_t* __restrict__ q,
+                                                    uint64_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  Pt a = pt_load52(p + 20 * i);
+  Pt r;
+  if (OP == PT_ADD) {
+    Pt b = pt_load52(q + 20 * i);
+    r = pt_add_ref_normal(a, b);
+  } else if (OP == PT_SUB) {
+    Pt b = pt_neg(pt_load52(q + 20 * i));   // Sub = self + (-other), edwards.rs:512
+    r = pt_add_ref_normal(a, b);
+  } else if (OP == PT_DOUBLE) {
+    r = pt_add_ref_normal(a, a);            // Double = self + self, edwards.rs:589-591
+  } else {
+    r = pt_neg(a);
+  }
+  pt_store52(out + 20 * i, r);
+}
+
+// ---- Ristretto equality (ristretto.rs:166-176) -----------------------------------------------------------
+__global__ void __launch_bounds__(TPB) ristretto_eq_kernel(const uint64_t* __restrict__ p, const uint64_t* __restrict__ q,
+                                                           uint8_t* __restrict__ eq, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  typedef ModP M;
+  Fe X1 = fe_load52(p + 20 * i), Y1 = fe_load52(p + 20 * i + 5);
+  Fe X2 = fe_load52(q + 20 * i), Y2 = fe_load52(q + 20 * i + 5);
+  // a common factor 1/R on both sides does not change equality
+  bool e1 = fe_eq(mont_mul<M>(X1, Y2), mont_mul<M>(Y1, X2));
+  bool e2 = fe_eq(mont_mul<M>(X1, X2), mont_mul<M>(Y1, Y2));
+  eq[i] = (e1 || e2) ? 1 : 0;
+}
+
+// ---- K3 strict: [s]P with the reference's LSB-first double_and_add (edwards.rs:102-120), limb-exact ----------
+// The loop body has ONE inlined point addition: phase 0 is "Q += N if the bit is set", phase 1 is "N += N".
+__global__ void __launch_bounds__(128) scalar_mul_strict_kernel(const uint64_t* __restrict__ points,
+                                                                const uint64_t* __restrict__ scalars,
+                                                                uint64_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+  const bool live = i < n;
+  size_t ii = live ? i : 0;
+  Pt N = pt_to_mont(pt_load52(points + 20 * ii));
+  Fe s = fe_load52(scalars + 5 * ii);
+  if (!live) { for (int k = 0; k < 8; k++) s.w[k] = 0; }
+  Pt Q = pt_identity_mont();
+  while (__any_sync(0xffffffffu, !fe_is_zero(s))) {
+    const bool nz = !fe_is_zero(s);
+    const bool odd = (s.w[0] & 1u) != 0;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+      if (phase == 0 && !__any_sync(0xffffffffu, odd)) continue;
+      Pt lhs = (phase == 0) ? Q : N;
+      Pt r = pt_add_ref(lhs, N);
+      if (phase == 0) { if (odd) Q = r; }
+      else            { if (nz) N = r; }
+    }
+    // n = n.half_without_mod()   scalar.rs:562-574
+#pragma unroll
+    for (int k = 0; k < 7; k++) s.w[k] = (s.w[k] >> 1) | (s.w[k + 1] << 31);
+    s.w[7] >>= 1;
+  }
+  if (live) pt_store52(out + 20 * i, pt_from_mont(Q));
+}
+
+// ---- K3 fast: signed 4-bit fixed window, dedicated doubling, table of cached multiples in shared memory --------
+// digits d_j in [-8, 8), s = sum d_j 16^j; table holds 1P..8P in cached form; 63 windows cover 252 bits (s < L < 2^250).
+constexpr int SM_FAST_TPB = 64;
+__global__ void __launch_bounds__(SM_FAST_TPB) scalar_mul_fast_kernel(const uint64_t* __restrict__ points,
+                                                                      const uint64_t* __restrict__ scalars,
+                                                                      uint64_t* __restrict__ out, size_t n) {
+  // table[e][word-slot][thread]: conflict-free, each thread only touches its own column
+  extern __shared__ uint32_t tbl[];   // 8 entries * 32 words * SM_FAST_TPB threads
+  size_t i = (size_t)blockIdx.x * SM_FAST_TPB + threadIdx.x;
+  const bool live = i < n;
+  size_t ii = live ? i : 0;
+  const int tx = threadIdx.x;
+  Pt P = pt_to_mont(pt_load52(points + 20 * ii));
+  Fe s = fe_load52(scalars + 5 * ii);
+
+  auto store_entry = [&](int e, const PtCached& c) {
+    uint32_t* base = tbl + (size_t)e * 32 * SM_FAST_TPB + tx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      base[(k) * SM_FAST_TPB] = c.YpX.w[k];
+      base[(8 + k) * SM_FAST_TPB] = c.YmX.w[k];
+      base[(16 + k) * SM_FAST_TPB] = c.Z.w[k];
+      base[(24 + k) * SM_FAST_TPB] = c.T2d.w[k];
+    }
+  };
+  auto load_entry = [&](int e) {
+    PtCached c;
+    const uint32_t* base = tbl + (size_t)e * 32 * SM_FAST_TPB + tx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      c.YpX.w[k] = base[(k) * SM_FAST_TPB];
+      c.YmX.w[k] = base[(8 + k) * SM_FAST_TPB];
+      c.Z.w[k] = base[(16 + k) * SM_FAST_TPB];
+      c.T2d.w[k] = base[(24 + k) * SM_FAST_TPB];
+    }
+    return c;
+  };
+
+  {  // table: e -> (e+1) P
+    PtCached c1 = pt_to_cached(P);
+    store_entry(0, c1);
+    Pt acc = P;
+#pragma unroll 1
+    for (int e = 1; e < 8; e++) {
+      acc = pt_add_cached(acc, c1);
+      store_entry(e, pt_to_cached(acc));
+    }
+  }
+
+  // signed digits, most significant first.  carry-propagating recode done on the fly from the top is awkward, so
+  // recode from the bottom into a packed 4-bit array (63 digits + final carry digit).
+  uint32_t dig[8];   // 64 nibbles, two's-complement 4-bit digits
+  {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint32_t w = s.w[k], o = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        uint32_t d = ((w >> (4 * j)) & 15u) + carry;   // 0..16
+        carry = (d >= 8u) ? 1u : 0u;                   // d in [8,16] -> d - 16, carry 1
+        o |= (d & 15u) << (4 * j);
+      }
+      dig[k] = o;
+    }
+    // s < 2^250 so the top nibble (bits 252..255) is 0 before the carry and the final carry is always 0
+  }
+
+  Pt Q = pt_identity_mont();
+#pragma unroll 1
+  for (int j = 63; j >= 0; j--) {
+    if (j != 63) {
+      Q = pt_double_fast(Q); Q = pt_double_fast(Q); Q = pt_double_fast(Q); Q = pt_double_fast(Q);
+    }
+    uint32_t nib = (dig[j >> 3] >> (4 * (j & 7))) & 15u;
+    int d = (nib >= 8u) ? (int)nib - 16 : (int)nib;
+    int mag = d < 0 ? -d : d;
+    if (__any_sync(0xffffffffu, mag != 0)) {
+      PtCached c = load_entry(mag ? mag - 1 : 0);
+      if (d < 0) c = pt_cached_neg(c);
+      Pt r = pt_add_cached(Q, c);
+      if (mag != 0) Q = r;
+    }
+  }
+  if (live) pt_store52(out + 20 * i, pt_from_mont(Q));
+}
+
+// ---- fold k points in index order with the reference Add (one thread; k is the number of ranks) ---------------
+__global__ void point_fold_kernel(const uint64_t* __restrict__ pts, size_t k, uint64_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (k == 0) { pt_store52(out, pt_from_mont(pt_identity_mont())); return; }
+  Pt acc = pt_to_mont(pt_load52(pts));
+  for (size_t j = 1; j < k; j++) acc = pt_add_ref(acc, pt_to_mont(pt_load52(pts + 20 * j)));
+  pt_store52(out, pt_from_mont(acc));
+}
+
+inline unsigned grid_for(size_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+template <class M, int OP>
+int32_t launch_fe(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  if (n == 0) return ZC_OK;
+  fe_op_kernel<M, OP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(a, b, out, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+template <int OP>
+int32_t launch_pt(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
+  if (n == 0) return ZC_OK;
+  pt_op_kernel<OP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(p, q, out, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+
+constexpr size_t MAX_N = (size_t)1 << 31;
+
+// host-pointer wrapper: copy in (up to 2 inputs), run, copy out, synchronise
+template <class F>
+int32_t host_binary(zc_ctx* ctx, const void* a, size_t a_bytes, const void* b, size_t b_bytes, void* out, size_t out_bytes, F run) {
+  void *da = nullptr, *db = nullptr, *dout = nullptr;
+  int32_t rc;
+  if ((rc = zc_scratch(ctx, 0, a_bytes, &da))) return rc;
+  if (b) { if ((rc = zc_scratch(ctx, 1, b_bytes, &db))) return rc; }
+  if ((rc = zc_scratch(ctx, 2, out_bytes, &dout))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(da, a, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (b) ZC_CUDA(ctx, cudaMemcpyAsync(db, b, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = run(da, db, dout))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZC_OK;
+}
+
+}  // namespace
+
+// ================================================= C ABI =================================================
+#define ZC_CHECK_CTX(ctx) do { if (!(ctx)) return ZC_ERR_NULL; ZC_CUDA(ctx, cudaSetDevice((ctx)->device)); } while (0)
+#define ZC_CHECK_PTR(ctx, cond) do { if (!(cond)) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument"); } while (0)
+#define ZC_CHECK_N(ctx, n) do { if ((n) > MAX_N) return zc_fail(ctx, ZC_ERR_SIZE, "n exceeds 2^31"); } while (0)
+
+extern "C" {
+
+const char* zc_version(void) { return "zerocaf_b200 0.1 (sm_100a)"; }
+
+int32_t zc_ctx_create(int32_t device, void* stream, zc_ctx** out) {
+  if (!out) return ZC_ERR_NULL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return -(int32_t)e;          // no CUDA device: there is no CPU fallback
+  if (device < 0 || device >= count) return ZC_ERR_SIZE;
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return -(int32_t)e;
+  zc_ctx* ctx = new zc_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return -(int32_t)e; }
+    ctx->own_stream = true;
+  }
+  cudaFuncSetAttribute(scalar_mul_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * SM_FAST_TPB * 4);
+  *out = ctx;
+  return ZC_OK;
+}
+
+int32_t zc_ctx_destroy(zc_ctx* ctx) {
+  if (!ctx) return ZC_ERR_NULL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 6; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->msm_ws) cudaFree(ctx->msm_ws);
+  if (ctx->gather_buf) cudaFree(ctx->gather_buf);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return ZC_OK;
+}
+
+int32_t zc_ctx_sync(zc_ctx* ctx) {
+  ZC_CHECK_CTX(ctx);
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZC_OK;
+}
+
+const char* zc_last_error_string(zc_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+uint64_t zc_ctx_launch_count(zc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t zc_host_alloc(size_t bytes, void** out) {
+  if (!out) return ZC_ERR_NULL;
+  cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+  return e == cudaSuccess ? ZC_OK : -(int32_t)e;
+}
+int32_t zc_host_free(void* p) {
+  cudaError_t e = cudaFreeHost(p);
+  return e == cudaSuccess ? ZC_OK : -(int32_t)e;
+}
+
+// ---- field / scalar element-wise ------------------------------------------------------------------------
+#define ZC_DEFINE_BIN(NAME, MOD, OP)                                                                              \
+  int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {                \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, a && b && out);                                                                             \
+    return launch_fe<MOD, OP>(ctx, a, b, out, n);                                                                 \
+  }                                                                                                               \
+  int32_t NAME(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {                      \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, a && b && out);                                                                             \
+    return host_binary(ctx, a, n * 40, b, n * 40, out, n * 40, [&](void* da, void* db, void* dout) {              \
+      return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, n);               \
+    });                                                                                                           \
+  }
+#define ZC_DEFINE_UN(NAME, MOD, OP)                                                                               \
+  int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t n) {                                   \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, a && out);                                                                                  \
+    return launch_fe<MOD, OP>(ctx, a, nullptr, out, n);                                                           \
+  }                                                                                                               \
+  int32_t NAME(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t n) {                                         \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, a && out);                                                                                  \
+    return host_binary(ctx, a, n * 40, nullptr, 0, out, n * 40, [&](void* da, void*, void* dout) {                \
+      return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, n);                           \
+    });                                                                                                           \
+  }
+
+ZC_DEFINE_BIN(zc_fe_mul_batch, ModP, OP_MUL)
+ZC_DEFINE_BIN(zc_fe_add_batch, ModP, OP_ADD)
+ZC_DEFINE_BIN(zc_fe_sub_batch, ModP, OP_SUB)
+ZC_DEFINE_UN(zc_fe_square_batch, ModP, OP_SQUARE)
+ZC_DEFINE_UN(zc_fe_neg_batch, ModP, OP_NEG)
+ZC_DEFINE_BIN(zc_scalar_mul_batch, ModL, OP_MUL)
+ZC_DEFINE_BIN(zc_scalar_add_batch, ModL, OP_ADD)
+ZC_DEFINE_BIN(zc_scalar_sub_batch, ModL, OP_SUB)
+ZC_DEFINE_UN(zc_scalar_square_batch, ModL, OP_SQUARE)
+ZC_DEFINE_UN(zc_scalar_neg_batch, ModL, OP_NEG)
+
+int32_t zc_fe_mul_square_batch_dev(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* prod, uint64_t* sq, size_t n) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, a && b && prod && sq);
+  fe_mul_square_kernel<ModP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(a, b, prod, sq, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_fe_mul_square_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* prod, uint64_t* sq, size_t n) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, a && b && prod && sq);
+  void *da, *db, *dp, *ds;
+  int32_t rc;
+  if ((rc = zc_scratch(ctx, 0, n * 40, &da))) return rc;
+  if ((rc = zc_scratch(ctx, 1, n * 40, &db))) return rc;
+  if ((rc = zc_scratch(ctx, 2, n * 40, &dp))) return rc;
+  if ((rc = zc_scratch(ctx, 3, n * 40, &ds))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(da, a, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  ZC_CUDA(ctx, cudaMemcpyAsync(db, b, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = zc_fe_mul_square_batch_dev(ctx, (uint64_t*)da, (uint64_t*)db, (uint64_t*)dp, (uint64_t*)ds, n))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(prod, dp, n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaMemcpyAsync(sq, ds, n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZC_OK;
+}
+
+// ---- points ----------------------------------------------------------------------------------------------
+#define ZC_DEFINE_PT_BIN(NAME, OP)                                                                                \
+  int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {                \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, p && q && out);                                                                             \
+    return launch_pt<OP>(ctx, p, q, out, n);                                                                      \
+  }                                                                                                               \
+  int32_t NAME(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {                      \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, p && q && out);                                                                             \
+    return host_binary(ctx, p, n * 160, q, n * 160, out, n * 160, [&](void* da, void* db, void* dout) {           \
+      return launch_pt<OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, n);                    \
+    });                                                                                                           \
+  }
+#define ZC_DEFINE_PT_UN(NAME, OP)                                                                                 \
+  int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* p, uint64_t* out, size_t n) {                                   \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, p && out);                                                                                  \
+    return launch_pt<OP>(ctx, p, nullptr, out, n);                                                                \
+  }                                                                                                               \
+  int32_t NAME(zc_ctx* ctx, const uint64_t* p, uint64_t* out, size_t n) {                                         \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, p && out);                                                                                  \
+    return host_binary(ctx, p, n * 160, nullptr, 0, out, n * 160, [&](void* da, void*, void* dout) {              \
+      return launch_pt<OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, n);                                \
+    });                                                                                                           \
+  }
+
+ZC_DEFINE_PT_BIN(zc_point_add_batch, PT_ADD)
+ZC_DEFINE_PT_BIN(zc_point_sub_batch, PT_SUB)
+ZC_DEFINE_PT_UN(zc_point_double_batch, PT_DOUBLE)
+ZC_DEFINE_PT_UN(zc_point_neg_batch, PT_NEG)
+
+int32_t zc_ristretto_eq_batch_dev(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint8_t* eq, size_t n) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, p && q && eq);
+  ristretto_eq_kernel<<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(p, q, eq, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_ristretto_eq_batch(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint8_t* eq, size_t n) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, p && q && eq);
+  return host_binary(ctx, p, n * 160, q, n * 160, eq, n, [&](void* da, void* db, void* dout) {
+    return zc_ristretto_eq_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint8_t*)dout, n);
+  });
+}
+
+int32_t zc_point_scalar_mul_batch_dev(zc_ctx* ctx, const uint64_t* points, const uint64_t* scalars, uint64_t* out, size_t n, int32_t mode) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (mode != ZC_SCALAR_MUL_STRICT && mode != ZC_SCALAR_MUL_FAST) return zc_fail(ctx, ZC_ERR_MODE, "unknown scalar-mul mode");
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, points && scalars && out);
+  if (mode == ZC_SCALAR_MUL_STRICT) {
+    scalar_mul_strict_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(points, scalars, out, n);
+  } else {
+    scalar_mul_fast_kernel<<<grid_for(n, SM_FAST_TPB), SM_FAST_TPB, 8 * 32 * SM_FAST_TPB * 4, ctx->stream>>>(points, scalars, out, n);
+  }
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_point_scalar_mul_batch(zc_ctx* ctx, const uint64_t* points, const uint64_t* scalars, uint64_t* out, size_t n, int32_t mode) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (mode != ZC_SCALAR_MUL_STRICT && mode != ZC_SCALAR_MUL_FAST) return zc_fail(ctx, ZC_ERR_MODE, "unknown scalar-mul mode");
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, points && scalars && out);
+  return host_binary(ctx, points, n * 160, scalars, n * 40, out, n * 160, [&](void* da, void* db, void* dout) {
+    return zc_point_scalar_mul_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, n, mode);
+  });
+}
+
+int32_t zc_point_fold_dev(zc_ctx* ctx, const uint64_t* points_dev, size_t k, uint64_t* out_point_dev) {
+  ZC_CHECK_CTX(ctx);
+  ZC_CHECK_PTR(ctx, out_point_dev && (k == 0 || points_dev));
+  point_fold_kernel<<<1, 32, 0, ctx->stream>>>(points_dev, k, out_point_dev);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+/*
+ * zerocaf_b200.h -- C ABI of libzerocaf_b200.so: the batched, B200-native (sm_100a) backend for the arithmetic hot
+ * path of dusk-network/dusk-zerocaf.
+ *
+ * The reference crate has NO FFI / plugin boundary: its seam is the backend type alias
+ *     pub type FieldElement = backend::u64::field::FieldElement;     /root/reference/src/field.rs:83-91
+ *     pub type Scalar       = backend::u64::scalar::Scalar;          /root/reference/src/scalar.rs:68-76
+ * selected by a cargo feature (/root/reference/Cargo.toml:41-45, src/backend/mod.rs:9-16).  A `cuda_backend` feature
+ * binds the entry points below (see INTEGRATION.md for the Rust `extern "C"` block and the trait impls).
+ *
+ * Data layout at the boundary == the reference's in-memory types:
+ *   FieldElement / Scalar : uint64_t[5], radix-2^52 limbs, little-endian limb order, canonical (< modulus, limbs < 2^52)
+ *                           /root/reference/src/backend/u64/field.rs:31-32, scalar.rs:26-27
+ *   EdwardsPoint / RistrettoPoint : uint64_t[20] = X|Y|Z|T          /root/reference/src/edwards.rs:336-342,
+ *                                                                    /root/reference/src/ristretto.rs:157-158
+ * Arrays are AoS with 40-byte (field/scalar) and 160-byte (point) stride.  Inputs must be canonical; outputs are.
+ *
+ * Every function returns a status: 0 = ok, > 0 = argument error (ZC_ERR_*), < 0 = -(cudaError_t) / NCCL failure.
+ * Nothing aborts or throws across the boundary (the reference panics instead: scalar.rs:465, field.rs:285).
+ * There is no CPU fallback: without a CUDA device zc_ctx_create fails with a negative status.
+ *
+ * Plain functions take HOST pointers (copy in, compute, copy out, synchronous).  `_dev` twins take DEVICE pointers,
+ * enqueue on the context's stream and return without synchronising (zc_ctx_sync waits).  `out` may alias an input
+ * exactly (in place) but must not partially overlap.  A context is bound to one device and one stream and is not
+ * thread-safe; distinct contexts are independent.
+ */
+#ifndef ZEROCAF_B200_H
+#define ZEROCAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZC_OK                0
+#define ZC_ERR_NULL          1   /* null pointer argument */
+#define ZC_ERR_SIZE          2   /* n too large / zero where not allowed */
+#define ZC_ERR_MODE          3   /* unknown mode / window */
+#define ZC_ERR_NONCANONICAL  4   /* validation requested and an input is not canonical */
+#define ZC_ERR_STATE         5   /* context misuse (e.g. sharded call without a communicator) */
+
+#define ZC_SCALAR_MUL_STRICT 0   /* LSB-first double-and-add with add-as-double: limb-exact vs edwards.rs:102-120 */
+#define ZC_SCALAR_MUL_FAST   1   /* signed fixed-window, dedicated doubling: same group element, other representative */
+
+typedef struct zc_ctx zc_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+const char *zc_version(void);
+/* stream: a cudaStream_t to enqueue on, or NULL for a stream owned by the context. */
+int32_t zc_ctx_create(int32_t device, void *stream, zc_ctx **out);
+int32_t zc_ctx_destroy(zc_ctx *ctx);
+int32_t zc_ctx_sync(zc_ctx *ctx);
+const char *zc_last_error_string(zc_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t zc_ctx_launch_count(zc_ctx *ctx);
+/* pinned host memory for callers that want full-speed copies */
+int32_t zc_host_alloc(size_t bytes, void **out);
+int32_t zc_host_free(void *p);
+
+/* ---- FieldElement batch ops: out[i] = a[i] (op) b[i] mod p ------------------------------------------------ */
+/* replaces Mul  field.rs:250-275 */
+int32_t zc_fe_mul_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* replaces Square field.rs:302-315 */
+int32_t zc_fe_square_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+/* replaces Add  field.rs:191-215 */
+int32_t zc_fe_add_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* replaces Sub  field.rs:217-248 */
+int32_t zc_fe_sub_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* replaces Neg  field.rs:170-189 */
+int32_t zc_fe_neg_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+/* BASELINE config 2: prod[i] = a[i]*b[i], sq[i] = a[i]^2, both fully reduced, one launch */
+int32_t zc_fe_mul_square_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *prod, uint64_t *sq, size_t n);
+
+int32_t zc_fe_mul_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_fe_square_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_fe_add_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_fe_sub_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_fe_neg_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_fe_mul_square_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *prod, uint64_t *sq, size_t n);
+
+/* ---- Scalar batch ops (mod L): replaces scalar.rs Mul :247-270, Square :272-283, Add :184-208, Sub :210-245, Neg --- */
+int32_t zc_scalar_mul_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_scalar_square_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_scalar_add_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_scalar_sub_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_scalar_neg_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+
+int32_t zc_scalar_mul_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_scalar_square_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_scalar_add_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_scalar_sub_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_scalar_neg_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+
+/* ---- EdwardsPoint / RistrettoPoint batch ops (limb-exact representatives) ---------------------------------- */
+/* replaces Add edwards.rs:465-501 / ristretto.rs:248-276 */
+int32_t zc_point_add_batch(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint64_t *out, size_t n);
+/* replaces Sub edwards.rs:503-545 / ristretto.rs:278-312 */
+int32_t zc_point_sub_batch(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint64_t *out, size_t n);
+/* replaces Double edwards.rs:579-592 / ristretto.rs:314-328  (= P + P with the Add formulas) */
+int32_t zc_point_double_batch(zc_ctx *ctx, const uint64_t *p, uint64_t *out, size_t n);
+/* replaces Neg edwards.rs:440-463 / ristretto.rs:224-246 */
+int32_t zc_point_neg_batch(zc_ctx *ctx, const uint64_t *p, uint64_t *out, size_t n);
+/* replaces Mul<&Scalar> edwards.rs:547-577 / ristretto.rs:330-392 (double_and_add edwards.rs:102-120) */
+int32_t zc_point_scalar_mul_batch(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, uint64_t *out, size_t n, int32_t mode);
+/* Ristretto equality ristretto.rs:166-176: eq[i] = 1 iff X1*Y2 == Y1*X2 or X1*X2 == Y1*Y2 */
+int32_t zc_ristretto_eq_batch(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint8_t *eq, size_t n);
+
+int32_t zc_point_add_batch_dev(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint64_t *out, size_t n);
+int32_t zc_point_sub_batch_dev(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint64_t *out, size_t n);
+int32_t zc_point_double_batch_dev(zc_ctx *ctx, const uint64_t *p, uint64_t *out, size_t n);
+int32_t zc_point_neg_batch_dev(zc_ctx *ctx, const uint64_t *p, uint64_t *out, size_t n);
+int32_t zc_point_scalar_mul_batch_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, uint64_t *out, size_t n, int32_t mode);
+int32_t zc_ristretto_eq_batch_dev(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint8_t *eq, size_t n);
+
+/* ---- multi-scalar multiplication  out = sum_i [s_i] P_i  (new capability; the reference has none) ---
+ * Semantics = fold(Add, identity, [double_and_add(P_i, s_i)]) (edwards.rs:102-120, 465-489) as a GROUP ELEMENT: the
+ * returned (X:Y:Z:T) is a valid representative, compare with affine / Ristretto equality.  Pippenger with signed
+ * `window_bits`-bit digits (8..16); n = 0 returns the identity (0,1,1,0). */
+int32_t zc_msm(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point);
+int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev);
+
+/* Bucket-window-sharded MSM: a collective, every rank calls it with the same (points, scalars, n, window_bits), all
+ * resident on its own device.  Rank r accumulates windows w = r (mod nranks), scales its window sums and folds them to
+ * one partial point; the partial points are exchanged with ONE ncclAllGather on the context's stream and folded in rank
+ * order on every rank, so all ranks return identical bits.  `nccl_comm` is an ncclComm_t created by the caller
+ * (e.g. from an ncclUniqueId distributed with torch.distributed); libnccl is resolved at run time with dlopen. */
+int32_t zc_ctx_set_nccl(zc_ctx *ctx, void *nccl_comm, int32_t rank, int32_t nranks);
+int32_t zc_nccl_unique_id(uint8_t id_out[128]);
+int32_t zc_nccl_comm_init(const uint8_t id[128], int32_t rank, int32_t nranks, void **comm_out);
+int32_t zc_nccl_comm_destroy(void *comm);
+int32_t zc_msm_sharded_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev);
+/* the local half only (no exchange): rank r's partial point, for tests of the sharding logic without NCCL */
+int32_t zc_msm_partial_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits,
+                           int32_t rank, int32_t nranks, uint64_t *out_point_dev);
+/* fold k partial points in index order with the Add formulas (edwards.rs:465-489) */
+int32_t zc_point_fold_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t k, uint64_t *out_point_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEROCAF_B200_H */

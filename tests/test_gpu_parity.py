@@ -1,0 +1,302 @@
+"""GPU parity tests proper: every call goes through the C ABI of libzerocaf_b200.so and is compared, bit for
+bit, with the CPU oracle (oracle/) on the same seeded inputs and with the reference's own golden vectors
+(tests/golden/reference_kats.json).  Point results of the fast paths / MSM are compared canonically."""
+import numpy as np
+import pytest
+
+from conftest import SEED, kat_arr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zc():
+    import dusk_zerocaf_b200 as z
+    z.default_context()
+    return z
+
+
+def F(kats, n): return kat_arr(kats, "field", n)
+def S(kats, n): return kat_arr(kats, "scalar", n)
+def E(kats, n): return kat_arr(kats, "edwards", n)
+def C(kats, n): return kat_arr(kats, "constants", n)
+
+
+def synth_points(oracle, stream, n, threads=8):
+    """P_i = [r_i] B with r_i synthetic scalars; computed by the ORACLE (test input only)."""
+    B = None
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")) as f:
+        k = json.load(f)
+    B = np.array(k["constants"]["items"]["BASEPOINT"]["values"], dtype=np.uint64)
+    r = oracle.synth_scalar(SEED, stream, 0, n)
+    return oracle.pt_scalar_mul_batch(np.tile(B, (n, 1)), r, threads=threads)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# field KATs through the ABI (reference field.rs:1136-1240, 1492-1522)
+# ---------------------------------------------------------------------------------------------------------
+def test_field_kats(zc, kats):
+    b = zc.batch
+    A, B, Cc = F(kats, "A"), F(kats, "B"), F(kats, "C")
+    assert np.array_equal(b.fe_mul(A, B)[0], F(kats, "A_TIMES_B"))       # mul_with_modulo field.rs:1202
+    assert np.array_equal(b.fe_mul(A, Cc)[0], F(kats, "A_TIMES_C"))      # mul_without_modulo :1210
+    assert np.array_equal(b.fe_square(A)[0], F(kats, "A_SQUARE"))        # square :1218
+    assert np.array_equal(b.fe_square(B)[0], F(kats, "B_SQUARE"))
+    assert np.array_equal(b.fe_add(A, B)[0], F(kats, "A_PLUS_B"))        # addition_with_modulo :1136
+    assert np.array_equal(b.fe_sub(A, B)[0], F(kats, "A_MINUS_B"))       # subtraction :1169
+    assert np.array_equal(b.fe_sub(B, A)[0], F(kats, "B_MINUS_A"))
+    assert np.array_equal(b.fe_neg(A)[0], F(kats, "MINUS_A"))            # neg :1492
+    assert np.array_equal(b.fe_neg(B)[0], F(kats, "MINUS_B"))
+    zero, one = np.zeros(5, np.uint64), np.array([1, 0, 0, 0, 0], np.uint64)
+    minus_one = b.fe_neg(one)[0]
+    assert np.array_equal(b.fe_add(minus_one, one)[0], zero)             # -1 + 1 = 0
+    assert np.array_equal(b.fe_square(zero)[0], zero)                    # square_zero_and_identity :1231
+    assert np.array_equal(b.fe_square(one)[0], one)
+    assert np.array_equal(b.fe_neg(zero)[0], zero)
+
+
+def test_scalar_kats(zc, kats):
+    b = zc.batch
+    X, Y = S(kats, "X"), S(kats, "Y")
+    assert np.array_equal(b.scalar_mul(X, Y)[0], S(kats, "X_TIMES_Y"))   # scalar_mul scalar.rs:860
+    assert np.array_equal(b.scalar_square(Y)[0], S(kats, "Y_SQ"))        # square :893
+    A, B = S(kats, "A"), S(kats, "B")
+    assert np.array_equal(b.scalar_sub(A, B)[0], S(kats, "AB"))          # sub :818
+    assert np.array_equal(b.scalar_sub(B, A)[0], S(kats, "BA"))
+
+
+def test_point_kats(zc, kats, oracle):
+    b = zc.batch
+    P1, P2 = E(kats, "P1_EXTENDED"), E(kats, "P2_EXTENDED")
+    assert np.array_equal(b.point_add(P1, P2)[0], E(kats, "P4_EXTENDED"))   # extended_point_addition edwards.rs:1388 (limb-exact)
+    dbl = b.point_double(P1)[0]
+    assert oracle.pt_eq(dbl, E(kats, "P3_EXTENDED"))                        # extended_point_doubling :1394 (affine)
+    assert np.array_equal(dbl, oracle.pt_double(P1))                        # limb-exact vs Double = self + self
+    assert np.array_equal(b.point_neg(P1)[0], oracle.pt_neg(P1))
+    assert np.array_equal(b.point_sub(P1, P2)[0], oracle.pt_sub(P1, P2))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 1: 1k random FieldElement::mul, bit-exact
+# ---------------------------------------------------------------------------------------------------------
+def test_cfg1_1k_field_mul(zc, oracle):
+    a = oracle.synth_fe(SEED, 1, 0, 1000)
+    bb = oracle.synth_fe(SEED, 2, 0, 1000)
+    assert np.array_equal(zc.batch.fe_mul(a, bb), oracle.fe_mul_batch(a, bb))
+
+
+@pytest.mark.parametrize("n", [1, 31, 257, 100_003])
+def test_field_ops_random(zc, oracle, n):
+    b = zc.batch
+    a = oracle.synth_fe(SEED, 3, 0, n)
+    c = oracle.synth_fe(SEED, 4, 0, n)
+    # full-range operands too: a' = -a covers values up to p-1
+    na = oracle.fe_neg_batch(a)
+    for x, y in ((a, c), (na, c), (na, na)):
+        assert np.array_equal(b.fe_mul(x, y), oracle.fe_mul_batch(x, y))
+        assert np.array_equal(b.fe_add(x, y), oracle.fe_add_batch(x, y))
+        assert np.array_equal(b.fe_sub(x, y), oracle.fe_sub_batch(x, y))
+    assert np.array_equal(b.fe_square(na), oracle.fe_square_batch(na))
+    assert np.array_equal(b.fe_neg(a), na)
+    prod, sq = b.fe_mul_square(na, c)
+    assert np.array_equal(prod, oracle.fe_mul_batch(na, c))
+    assert np.array_equal(sq, oracle.fe_square_batch(na))
+
+
+def test_field_edge_values(zc, oracle):
+    p = 2**252 + 27742317777372353535851937790883648493
+    vals = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, 2**252 - 1, 2**252, 2**251, 2**128 - 1, 2**52, 2**52 - 1]
+    arr = np.array([oracle.int_to_limbs(v) for v in vals], dtype=np.uint64)
+    n = len(vals)
+    x = np.repeat(arr, n, axis=0)
+    y = np.tile(arr, (n, 1))
+    b = zc.batch
+    assert np.array_equal(b.fe_mul(x, y), oracle.fe_mul_batch(x, y))
+    assert np.array_equal(b.fe_add(x, y), oracle.fe_add_batch(x, y))
+    assert np.array_equal(b.fe_sub(x, y), oracle.fe_sub_batch(x, y))
+    assert np.array_equal(b.fe_square(arr), oracle.fe_square_batch(arr))
+
+
+def test_scalar_ops_random(zc, oracle):
+    b = zc.batch
+    n = 5000
+    a = oracle.synth_scalar(SEED, 5, 0, n)
+    c = oracle.synth_scalar(SEED, 6, 0, n)
+    na = oracle.sc_sub_batch(np.zeros_like(a), a)     # up to L-1
+    for x, y in ((a, c), (na, c), (na, na)):
+        assert np.array_equal(b.scalar_mul(x, y), oracle.sc_mul_batch(x, y))
+        assert np.array_equal(b.scalar_add(x, y), oracle.sc_add_batch(x, y))
+        assert np.array_equal(b.scalar_sub(x, y), oracle.sc_sub_batch(x, y))
+    assert np.array_equal(b.scalar_square(na), oracle.sc_square_batch(na))
+    assert np.array_equal(b.scalar_neg(a), na)
+
+
+def test_empty_and_inplace(zc, oracle):
+    b = zc.batch
+    e = np.zeros((0, 5), np.uint64)
+    assert b.fe_mul(e, e).shape == (0, 5)
+    assert b.point_add(np.zeros((0, 20), np.uint64), np.zeros((0, 20), np.uint64)).shape == (0, 20)
+    # in place: out aliases a
+    a = oracle.synth_fe(SEED, 7, 0, 1000)
+    c = oracle.synth_fe(SEED, 8, 0, 1000)
+    want = oracle.fe_mul_batch(a, c)
+    ctx = zc.default_context()
+    ctx.call("zc_fe_mul_batch", a, c, a, 1000)
+    assert np.array_equal(a, want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 3: point add / double, limb-exact
+# ---------------------------------------------------------------------------------------------------------
+def test_point_ops_random(zc, oracle):
+    b = zc.batch
+    n = 2048
+    P = synth_points(oracle, 10, n)
+    Q = synth_points(oracle, 11, n)
+    assert np.array_equal(b.point_add(P, Q), oracle.pt_add_batch(P, Q, threads=8))
+    assert np.array_equal(b.point_sub(P, Q), oracle.pt_sub_batch(P, Q, threads=8))
+    assert np.array_equal(b.point_double(P), oracle.pt_double_batch(P, threads=8))
+    assert np.array_equal(b.point_neg(P), oracle.pt_neg_batch(P))
+    # identity and self-inverse edge cases
+    I = np.tile(oracle.pt_identity(), (n, 1))
+    assert np.array_equal(b.point_add(P, I), oracle.pt_add_batch(P, I))
+    assert np.array_equal(b.point_add(I, I), oracle.pt_add_batch(I, I))
+    assert np.array_equal(b.point_sub(P, P), oracle.pt_sub_batch(P, P))
+    assert np.all(b.ristretto_eq(P, P) == 1)
+    assert np.all(b.ristretto_eq(b.point_add(P, Q), b.point_add(Q, P)) == 1)
+    assert not np.any(b.ristretto_eq(P, Q))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 4: variable-base scalar-mul; strict = limb-exact vs double_and_add, fast = canonical
+# ---------------------------------------------------------------------------------------------------------
+def test_scalar_mul_strict(zc, oracle, kats):
+    n = 300
+    P = synth_points(oracle, 12, n)
+    s = oracle.synth_scalar(SEED, 13, 0, n)
+    # edge scalars: 0, 1, 2, L-1, 2^249-1
+    L = 2**249 + 14490550575682688738086195780655237219
+    for j, v in enumerate([0, 1, 2, L - 1, 2**249 - 1, 8, 2**248]):
+        s[j] = oracle.int_to_limbs(v)
+    got = zc.batch.point_scalar_mul(P, s, mode=0)
+    want = oracle.pt_scalar_mul_batch(P, s, threads=8)
+    assert np.array_equal(got, want)
+    # unique_basepoint_test edwards.rs:1593: [L]B is the identity  (L as limbs is not a canonical scalar: use (L-1)B + B)
+    B = C(kats, "BASEPOINT")
+    lm1 = zc.batch.point_scalar_mul(B, oracle.int_to_limbs(L - 1), mode=0)[0]
+    assert oracle.pt_eq(zc.batch.point_add(lm1, B)[0], oracle.pt_identity())
+
+
+def test_scalar_mul_fast(zc, oracle):
+    n = 300
+    P = synth_points(oracle, 14, n)
+    s = oracle.synth_scalar(SEED, 15, 0, n)
+    L = 2**249 + 14490550575682688738086195780655237219
+    for j, v in enumerate([0, 1, 2, L - 1, 2**249 - 1, 8, 2**248, 7, 9, 0x8888888888888888]):
+        s[j] = oracle.int_to_limbs(v)
+    got = zc.batch.point_scalar_mul(P, s, mode=1)
+    want = oracle.pt_scalar_mul_batch(P, s, threads=8)
+    for i in range(n):
+        assert oracle.pt_eq(got[i], want[i]), i
+        assert oracle.pt_is_valid(got[i])
+    assert oracle.ris_compress(got[17]) == oracle.ris_compress(want[17])
+
+
+def test_ristretto_vectors_via_scalar_mul(zc, oracle, kats):
+    """valid_encoding_test_vectors ristretto.rs:541-579: compress([k]B), k = 0..15."""
+    B = C(kats, "BASEPOINT")
+    enc = kats["ristretto"]["encodings_of_small_multiples"] if "encodings_of_small_multiples" in kats["ristretto"] else None
+    ks = np.array([oracle.int_to_limbs(k) for k in range(16)], dtype=np.uint64)
+    for mode in (0, 1):
+        got = zc.batch.point_scalar_mul(np.tile(B, (16, 1)), ks, mode=mode)
+        acc = oracle.pt_identity()
+        for k in range(16):
+            assert oracle.ris_compress(got[k]) == oracle.ris_compress(acc), (mode, k)
+            if enc is not None:
+                assert oracle.ris_compress(got[k]).hex() == enc[k]
+            acc = oracle.pt_add(acc, B)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 5: MSM (derived oracle: fold of double_and_add)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,c", [(1, 16), (2, 8), (33, 8), (1000, 10), (4096, 13), (4096, 16)])
+def test_msm_vs_naive(zc, oracle, n, c):
+    P = synth_points(oracle, 20 + c, n)
+    s = oracle.synth_scalar(SEED, 40 + c, 0, n)
+    got = zc.batch.msm(P, s, window_bits=c)
+    want = oracle.msm_naive(P, s, threads=8)
+    assert oracle.pt_is_valid(got)
+    assert oracle.pt_eq(got, want)
+    assert oracle.ris_compress(got) == oracle.ris_compress(want)
+
+
+def test_msm_edges(zc, oracle, kats):
+    B = C(kats, "BASEPOINT")
+    L = 2**249 + 14490550575682688738086195780655237219
+    # empty -> identity
+    assert np.array_equal(zc.batch.msm(None, None), oracle.pt_identity())
+    # all scalars zero -> identity element
+    P = synth_points(oracle, 60, 64)
+    z = np.zeros((64, 5), np.uint64)
+    assert oracle.pt_eq(zc.batch.msm(P, z), oracle.pt_identity())
+    # all scalars one -> chained Add
+    one = np.tile(oracle.int_to_limbs(1), (64, 1))
+    acc = oracle.pt_identity()
+    for i in range(64):
+        acc = oracle.pt_add(acc, P[i])
+    assert oracle.pt_eq(zc.batch.msm(P, one), acc)
+    # extreme scalars: L-1 everywhere; repeated points (all digits collide in one bucket)
+    big = np.tile(oracle.int_to_limbs(L - 1), (64, 1))
+    assert oracle.pt_eq(zc.batch.msm(P, big), oracle.msm_naive(P, big, threads=8))
+    same = np.tile(B, (500, 1))
+    s = np.tile(oracle.int_to_limbs(0x7fff_8000_ffff_0001_8000), (500, 1))
+    assert oracle.pt_eq(zc.batch.msm(same, s, window_bits=16), oracle.msm_naive(same, s, threads=8))
+    # [L-1]B + [1]B = identity
+    pts = np.stack([B, B])
+    sc = np.stack([oracle.int_to_limbs(L - 1), oracle.int_to_limbs(1)])
+    assert oracle.pt_eq(zc.batch.msm(pts, sc), oracle.pt_identity())
+
+
+def test_msm_sharding_partials_fold_to_full(zc, oracle):
+    """The multi-GPU decomposition without NCCL: partial points of ranks 0..R-1 folded in rank order == full MSM."""
+    import torch
+    n, c = 3000, 16
+    P = synth_points(oracle, 70, n)
+    s = oracle.synth_scalar(SEED, 71, 0, n)
+    want = oracle.msm_naive(P, s, threads=8)
+    ctx = zc.default_context()
+    dP = torch.from_numpy(P.view(np.int64)).cuda()
+    dS = torch.from_numpy(s.view(np.int64)).cuda()
+    for R in (1, 2, 4, 8, 16):
+        parts = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
+        for r in range(R):
+            ctx.check(ctx._L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, r, R, parts[r].data_ptr()))
+        out = torch.zeros(20, dtype=torch.int64, device="cuda")
+        ctx.check(ctx._L.zc_point_fold_dev(ctx._h, parts.data_ptr(), R, out.data_ptr()))
+        ctx.sync()
+        got = out.cpu().numpy().view(np.uint64)
+        assert oracle.pt_eq(got, want), R
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side mirror types read like the reference's own tests
+# ---------------------------------------------------------------------------------------------------------
+def test_operator_surface(zc, kats, oracle):
+    A, B = zc.FieldElement(F(kats, "A")), zc.FieldElement(F(kats, "B"))
+    assert (A * B) == zc.FieldElement(F(kats, "A_TIMES_B"))
+    assert (A + B) == zc.FieldElement(F(kats, "A_PLUS_B"))
+    assert (A - B) == zc.FieldElement(F(kats, "A_MINUS_B"))
+    assert (-A) == zc.FieldElement(F(kats, "MINUS_A"))
+    assert A.square() == zc.FieldElement(F(kats, "A_SQUARE"))
+    P1, P2 = zc.EdwardsPoint(E(kats, "P1_EXTENDED")), zc.EdwardsPoint(E(kats, "P2_EXTENDED"))
+    assert np.array_equal((P1 + P2).limbs, E(kats, "P4_EXTENDED"))
+    assert P1.double() == zc.EdwardsPoint(E(kats, "P3_EXTENDED"))
+    eight = zc.Scalar(oracle.int_to_limbs(8))
+    assert P1 * eight == P1.double().double().double()                      # extended_double_and_add edwards.rs:1410
+    assert eight * P1 == P1 * eight
+    assert P1 + zc.EdwardsPoint.identity() == P1
+    assert (P1 - P1) == zc.EdwardsPoint.identity()
+    R1 = zc.RistrettoPoint(E(kats, "P1_EXTENDED"))
+    assert R1 + R1 == R1.double() and not (R1 == R1.double())
