@@ -206,7 +206,7 @@ def test_scalar_mul_fast(zc, oracle):
 def test_ristretto_vectors_via_scalar_mul(zc, oracle, kats):
     """valid_encoding_test_vectors ristretto.rs:541-579: compress([k]B), k = 0..15."""
     B = C(kats, "BASEPOINT")
-    enc = kats["ristretto"]["encodings_of_small_multiples"] if "encodings_of_small_multiples" in kats["ristretto"] else None
+    enc = kats["ristretto"]["small_multiples_hex"]
     ks = np.array([oracle.int_to_limbs(k) for k in range(16)], dtype=np.uint64)
     for mode in (0, 1):
         got = zc.batch.point_scalar_mul(np.tile(B, (16, 1)), ks, mode=mode)
