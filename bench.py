@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- zerocaf hot path on B200 (and the reference-equivalent CPU path beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on rank 0.  A "step" is one pass of BASELINE config 2 over one batch: 2^24 FieldElement pairs ->
+prod = a*b and sq = a^2, both fully reduced (2 x 2^24 253-bit field multiplications), one kernel launch.
+  value   field-muls/s, whole job, inputs resident in HBM (weak scaling: every rank owns its own 2^24 batch, the path is
+          element-wise and has no exchange step)
+  e2e     the same metric through the host-pointer C-ABI call (pinned host buffers, H2D + D2H inside the timed region)
+  roofline  algorithmic bytes (128 B per element pair: 2 x 32 in, 2 x 32 out) / kernel time vs measured HBM
+  extra   config 3 (2^22 point add / double), config 4 (2^20 scalar-mul), config 5 (2^20-point MSM, window 16, sharded by
+          bucket-window over the N ranks with one NCCL all-gather) as secondary keys of the same line.
+`--impl reference` times the CPU restatement of the reference's own algorithm (oracle/, kind "port": there is no Rust
+toolchain in this image) on all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FIELD = 1 << 24      # config 2
+N_POINT = 1 << 22      # config 3
+N_SMUL = 1 << 20       # config 4
+N_MSM = 1 << 20        # config 5
+MSM_WINDOW = 16
+BYTES_PER_PAIR = 128   # algorithmic bytes of one config-2 unit (canonical 32-byte encodings)
+METRIC = "253-bit field-muls/s (config 2: 2^24 mul+square+reduce per step)"
+UNIT = "field-muls/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference algorithm, all host threads, bounded sample
+# ------------------------------------------------------------------------------------------------------------
+def cpu_field_rate(n_sample, threads, repeats=1):
+    from oracle import oracle as o
+    from dusk_zerocaf_b200 import synth
+    o.build()
+    a = synth.synth_fe(1, 0, n_sample)
+    b = synth.synth_fe(2, 0, n_sample)
+    o.fe_mul_square_batch(a[:1024], b[:1024], threads=threads)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        o.fe_mul_square_batch(a, b, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 2.0 * n_sample / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = 1 << 22
+    for _ in range(max(args.warmup, 1)):
+        cpu_field_rate(1 << 18, cores)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_field_rate(n_sample, cores)
+        times.append(dt)
+    total = sum(times)
+    value = 2.0 * n_sample * args.steps / total
+    sample = f"2^22 of the 2^24 element pairs per step (mul+square), {cores} pthreads, oracle/zerocaf_oracle.c"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (radix-2^52 limbs, u128 products)", "data": "synthetic",
+        "config": {"workload": "config 2: batched FieldElement mul+square+reduce, CPU sample 2^22 pairs/step",
+                   "n_pairs_per_step": n_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import dusk_zerocaf_b200 as zc
+    from dusk_zerocaf_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: zerocaf_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = zc.Context(local, stream=stream.cuda_stream)
+    L = ctx._L
+
+    def timed(fn, steps, warmup):
+        """W warm-up calls, then K calls bracketed by barrier+sync, CUDA events on the launching stream, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), ctx.launches - l0
+
+    def dev_u64(arr):
+        return torch.from_numpy(arr.view(np.int64)).to(dev)
+
+    # ---- config 2 inputs (each rank its own batch: stream ids differ per rank) -----------------------------------
+    n = N_FIELD
+    pin = lambda shape: torch.empty(shape, dtype=torch.int64).pin_memory()
+    ha, hb, hp, hs = pin((n, 5)), pin((n, 5)), pin((n, 5)), pin((n, 5))
+    synth.synth_fe(1 + 16 * rank, 0, n, out=ha.numpy().view(np.uint64))
+    synth.synth_fe(2 + 16 * rank, 0, n, out=hb.numpy().view(np.uint64))
+    da, db = ha.to(dev), hb.to(dev)
+    dp, ds = torch.empty_like(da), torch.empty_like(da)
+    torch.cuda.synchronize()
+
+    def step_dev():
+        ctx.check(L.zc_fe_mul_square_batch_dev(ctx._h, da.data_ptr(), db.data_ptr(), dp.data_ptr(), ds.data_ptr(), n))
+
+    def step_e2e():
+        ctx.check(L.zc_fe_mul_square_batch(ctx._h, ha.data_ptr(), hb.data_ptr(), hp.data_ptr(), hs.data_ptr(), n))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_dev, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    value = 2.0 * n * world * args.steps / (ms * 1e-3)
+    kernel_ms = ms / args.steps
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e, _ = timed(step_e2e, e2e_steps, max(args.warmup, 3))
+    e2e_value = 2.0 * n * world * e2e_steps / (ms_e2e * 1e-3)
+    # device result of the e2e path must equal the resident path's (same inputs)
+    same = bool(torch.equal(hp.to(dev), dp) and torch.equal(hs.to(dev), ds))
+
+    peak, peak_src = measured_peak_gbs()
+    achieved = BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("fe_mul_square_kernel_bytes_per_launch")
+    except Exception:
+        pass
+
+    extra = {}
+    del ha, hb, hp, hs, dp, ds
+    if not args.skip_extra:
+        # ---- points for configs 3-5: P_i = [r_i]B from our own strict scalar-mul kernel ------------------
+        def make_points(stream_id, count):
+            sc = dev_u64(synth.synth_scalar(stream_id, 0, count))
+            base = dev_u64(np.tile(synth.BASEPOINT, (count, 1)))
+            out = torch.empty((count, 20), dtype=torch.int64, device=dev)
+            ctx.check(L.zc_point_scalar_mul_batch_dev(ctx._h, base.data_ptr(), sc.data_ptr(), out.data_ptr(), count, 0))
+            ctx.sync()
+            return out
+
+        k3 = max(3, args.steps // 2)
+        P = make_points(100, N_POINT)
+        Q = make_points(101, N_POINT)
+        O = torch.empty_like(P)
+        ms_add, _ = timed(lambda: ctx.check(L.zc_point_add_batch_dev(ctx._h, P.data_ptr(), Q.data_ptr(), O.data_ptr(), N_POINT)), k3, 3)
+        ms_dbl, _ = timed(lambda: ctx.check(L.zc_point_double_batch_dev(ctx._h, P.data_ptr(), O.data_ptr(), N_POINT)), k3, 3)
+        extra["config3_point_add"] = {
+            "n": N_POINT, "adds_per_s": N_POINT * world * k3 / (ms_add * 1e-3), "ms": ms_add / k3,
+            "doubles_per_s": N_POINT * world * k3 / (ms_dbl * 1e-3), "ms_double": ms_dbl / k3,
+            "hbm_frac_add": 384.0 * N_POINT / (ms_add / k3 * 1e-3) / 1e9 / peak}
+        # ---- config 4 ----------------------------------------------------------------------------------------------------
+        S = dev_u64(synth.synth_scalar(102, 0, N_SMUL))
+        P4, O4 = P[:N_SMUL].contiguous(), torch.empty((N_SMUL, 20), dtype=torch.int64, device=dev)
+        ms_strict, _ = timed(lambda: ctx.check(L.zc_point_scalar_mul_batch_dev(ctx._h, P4.data_ptr(), S.data_ptr(), O4.data_ptr(), N_SMUL, 0)), 2, 1)
+        ms_fast, _ = timed(lambda: ctx.check(L.zc_point_scalar_mul_batch_dev(ctx._h, P4.data_ptr(), S.data_ptr(), O4.data_ptr(), N_SMUL, 1)), 2, 1)
+        extra["config4_scalar_mul"] = {
+            "n": N_SMUL, "strict_per_s": N_SMUL * world * 2 / (ms_strict * 1e-3), "strict_ms": ms_strict / 2,
+            "fast_per_s": N_SMUL * world * 2 / (ms_fast * 1e-3), "fast_ms": ms_fast / 2,
+            "implied_point_adds_per_s_strict": 374.0 * N_SMUL * world * 2 / (ms_strict * 1e-3)}
+        # ---- config 5: MSM, strong scaling over the N ranks (bucket-window sharding + one NCCL all-gather) ----------
+        out_pt = torch.zeros(20, dtype=torch.int64, device=dev)
+        if world > 1:
+            def bcast(b):
+                obj = [b]
+                dist.broadcast_object_list(obj, src=0)
+                return obj[0]
+            ctx.init_nccl(rank, world, bcast)
+            msm_fn = lambda: ctx.check(L.zc_msm_sharded_dev(ctx._h, P4.data_ptr(), S.data_ptr(), N_MSM, MSM_WINDOW, out_pt.data_ptr()))
+        else:
+            msm_fn = lambda: ctx.check(L.zc_msm_dev(ctx._h, P4.data_ptr(), S.data_ptr(), N_MSM, MSM_WINDOW, out_pt.data_ptr()))
+        km = max(5, args.steps // 2)
+        ms_msm, l_msm = timed(msm_fn, km, 3)
+        identical = True
+        if world > 1:
+            g = [torch.zeros_like(out_pt) for _ in range(world)]
+            dist.all_gather(g, out_pt)
+            identical = all(bool(torch.equal(g[0], x)) for x in g)
+        extra["config5_msm"] = {
+            "n_points": N_MSM, "window_bits": MSM_WINDOW, "n_gpus": world, "msm_per_s": km / (ms_msm * 1e-3),
+            "ms_per_msm": ms_msm / km, "scaling": "strong", "launches_per_msm": l_msm / km,
+            "all_ranks_identical_bits": identical,
+            "sharding": "bucket-window (w mod N), one ncclAllGather of 160-B partial points + fixed-order fold" if world > 1 else "single GPU",
+            "hbm_frac": 160.0 * N_MSM / (ms_msm / km * 1e-3) / 1e9 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        ns = 1 << 23
+        v, dt = cpu_field_rate(ns, cores, repeats=3)
+        v1, dt1 = cpu_field_rate(1 << 21, 1, repeats=1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"2^23 of the 2^24 pairs (mul+square), best of 3, {cores} pthreads, oracle/zerocaf_oracle.c "
+                         f"(1:1 restatement of field.rs:250-262,302-315; no Rust toolchain here)",
+               "single_thread_value": v1}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 Montgomery words (IMAD.WIDE carry chains); ABI u64x5 radix-2^52", "data": "synthetic",
+            "config": {"workload": "config 2: batched 2^24 FieldElement mul+square+reduce per GPU, reference AoS [u64;5] layout in and out",
+                       "n_pairs_per_step_per_gpu": n, "l2_policy": "inputs larger than L2 (1.34 GB read + 1.34 GB written per step)",
+                       "parallelism": f"replicated element-wise x{world}, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "algorithmic bytes = 128 B per pair (32-B canonical encodings); the kernel moves 160 B per pair in the reference's 40-B limb layout"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 40 * world, "d2h_bytes_per_step": 2 * n * 40 * world,
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "matches_resident_path": same},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-extra", action="store_true", help="only the config-2 line (used under ncu)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" and not args.skip_extra else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
