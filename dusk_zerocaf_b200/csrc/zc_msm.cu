@@ -12,7 +12,8 @@
 //   digits   scalars -> signed c-bit digits for this rank's windows (+ per-bucket histogram, global atomics)
 //   scan     exclusive scan of the histogram per window (bucket start offsets)
 //   scatter  counting-sort scatter of (point index | sign) into bucket order
-//   accum    one thread per (window, bucket): serial sum of the bucket's run with 8M cached additions
+//   accum    one thread per 32-entry segment of the sorted list (balanced), 8M cached additions, prefetched gathers;
+//            fix/heavy stitch buckets that span segments
 //   reduce   sum_k (k+1) * B_k per window: multi-level chunked running sums (chunk m), tree sums per level
 //   combine  Horner over the levels and over this rank's windows with 2^c scalings -> one partial point
 //   exchange (sharded only) ncclAllGather of the partial points + fixed-order fold with the reference Add
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
 }
 
 // ---- scatter: counting sort of point indices into bucket order ----------------------------------------------------
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n, int nwl, int nb,
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n, size_t n_pad, int nwl, int nb,
                                                           uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= n * (size_t)nwl) return;
@@ -150,34 +151,155 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restr
   if (d == 0) return;
   uint32_t slot = (uint32_t)(d < 0 ? -d : d) - 1u;
   uint32_t pos = atomicAdd(&cursor[wl * nb + slot], 1u);
-  sorted[wl * n + pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+  sorted[wl * n_pad + pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
 }
 
-// ---- bucket accumulation: one thread per (window, bucket) ------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
-                                                        const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                        size_t n, int nwl, int nb, uint32_t* __restrict__ buckets) {
-  size_t g = (size_t)blockIdx.x * 128 + threadIdx.x;
-  if (g >= (size_t)nwl * nb) return;
-  size_t wl = g / nb;
-  uint32_t start = offs[g], cnt = hist[g];
-  const uint32_t* idx = sorted + wl * n + start;
-  Pt acc;
-  if (cnt == 0) {
-    acc = pt_identity_mont();
-  } else {
-    uint32_t e = idx[0];
-    PtCached c = ld_cached(cached + 32 * (size_t)(e & 0x7fffffffu));
-    if (e >> 31) c = pt_cached_neg(c);
-    acc = cached_to_pt(c);
-    for (uint32_t k = 1; k < cnt; k++) {
-      e = idx[k];
-      c = ld_cached(cached + 32 * (size_t)(e & 0x7fffffffu));
-      if (e >> 31) c = pt_cached_neg(c);
-      acc = pt_add_cached(acc, c);
+// ---- bucket accumulation, balanced: one thread per SEGMENT of SEG consecutive sorted entries ------------------------
+// A thread walks its SEG entries, summing runs of equal bucket.  A run that covers its whole bucket is stored straight
+// into buckets[]; a run cut by a segment boundary goes to the segment's H slot (run containing the segment's first
+// entry) or T slot (run containing its last entry, when that is a different run).  msm_fix_kernel then stitches the
+// buckets that span several segments.  Every thread does the same number of additions, whatever the digit
+// distribution (a top window with few, heavy buckets used to serialise thousands of additions in one thread).
+constexpr int SEG = 32;
+constexpr int ACC_TPB = 128;
+
+__device__ __forceinline__ PtCached ld_entry(const uint32_t* __restrict__ cached, uint32_t e) {
+  PtCached c = ld_cached(cached + 32 * (size_t)(e & 0x7fffffffu));
+  if (e >> 31) c = pt_cached_neg(c);
+  return c;
+}
+
+__global__ void __launch_bounds__(ACC_TPB) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
+                                                            const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
+                                                            size_t n_pad, int nseg, int nwl, int nb,
+                                                            uint32_t* __restrict__ buckets, uint32_t* __restrict__ partH,
+                                                            uint32_t* __restrict__ partT) {
+  __shared__ uint32_t idx_s[SEG * ACC_TPB];
+  const int tx = threadIdx.x;
+  size_t g = (size_t)blockIdx.x * ACC_TPB + tx;
+  if (g >= (size_t)nwl * nseg) return;
+  const size_t wl = g / nseg;
+  const uint32_t s = (uint32_t)(g - wl * nseg);
+  const uint32_t* woffs = offs + wl * nb;
+  const uint32_t* whist = hist + wl * nb;
+  const uint32_t nnz = woffs[nb - 1] + whist[nb - 1];
+  const uint32_t start = s * SEG;
+  if (start >= nnz) return;
+  const uint32_t end = min(start + SEG, nnz);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(sorted + wl * n_pad + start);
+#pragma unroll
+    for (int j = 0; j < SEG / 4; j++) {
+      uint4 v = src[j];
+      idx_s[(4 * j + 0) * ACC_TPB + tx] = v.x; idx_s[(4 * j + 1) * ACC_TPB + tx] = v.y;
+      idx_s[(4 * j + 2) * ACC_TPB + tx] = v.z; idx_s[(4 * j + 3) * ACC_TPB + tx] = v.w;
     }
   }
+  // bucket of the first entry: last b with offs[b] <= start  (upper_bound - 1)
+  uint32_t lo = 0, hi = (uint32_t)nb;
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (woffs[mid] <= start) lo = mid + 1; else hi = mid; }
+  uint32_t b = lo - 1;
+  uint32_t bbeg = woffs[b], bend = bbeg + whist[b];
+  uint32_t run_start = start;
+  uint32_t* bk = buckets + 32 * (wl * nb);
+  uint32_t* pH = partH + 32 * g;
+  uint32_t* pT = partT + 32 * g;
+
+  PtCached cur = ld_entry(cached, idx_s[tx]);
+  Pt acc = cached_to_pt(cur);
+  if (start + 1 < end) cur = ld_entry(cached, idx_s[ACC_TPB + tx]);
+#pragma unroll 1
+  for (uint32_t k = start + 1; k < end; k++) {
+    PtCached nxt = cur;
+    if (k + 1 < end) nxt = ld_entry(cached, idx_s[(k + 1 - start) * ACC_TPB + tx]);   // prefetch: independent of acc
+    if (k == bend) {
+      // flush the finished run
+      const bool complete = (run_start == bbeg);
+      st_pt(complete ? bk + 32 * (size_t)b : pH, acc);   // incomplete here <=> the run began before this segment (H slot)
+      do { b++; } while (whist[b] == 0);
+      bbeg = k; bend = k + whist[b];
+      run_start = k;
+      acc = cached_to_pt(cur);
+    } else {
+      acc = pt_add_cached(acc, cur);
+    }
+    cur = nxt;
+  }
+  {
+    const bool complete = (run_start == bbeg) && (end == bend);
+    uint32_t* dst = complete ? bk + 32 * (size_t)b : (run_start == start ? pH : pT);
+    st_pt(dst, acc);
+  }
+}
+
+// ---- stitch buckets that span several segments; write the identity into empty buckets -----------------------------
+// bucket range [o, e): s_first = o / SEG, s_last = (e-1) / SEG.  If s_first == s_last the run was complete and is already
+// in buckets[].  Otherwise  sum = (o == s_first*SEG ? H[s_first] : T[s_first]) + H[s_first+1] + ... + H[s_last].
+// Buckets with more than FIX_INLINE partials are queued for msm_heavy_kernel (one warp per bucket, tree sum).
+constexpr int FIX_INLINE = 6;
+__global__ void __launch_bounds__(128) msm_fix_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
+                                                      int nseg, int nwl, int nb, const uint32_t* __restrict__ partH,
+                                                      const uint32_t* __restrict__ partT, uint32_t* __restrict__ buckets,
+                                                      uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+  size_t g = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (g >= (size_t)nwl * nb) return;
+  const size_t wl = g / nb;
+  const uint32_t cnt = hist[g];
+  if (cnt == 0) { st_pt(buckets + 32 * g, pt_identity_mont()); return; }
+  const uint32_t o = offs[g], e = o + cnt;
+  const uint32_t s_first = o / SEG, s_last = (e - 1) / SEG;
+  if (s_first == s_last) return;
+  if (s_last - s_first + 1 > FIX_INLINE) {
+    uint32_t slot = atomicAdd(heavy_count, 1u);
+    heavy_list[slot] = (uint32_t)g;
+    return;
+  }
+  const uint32_t* H = partH + 32 * (wl * nseg);
+  const uint32_t* T = partT + 32 * (wl * nseg);
+  Pt acc = ld_pt((o == s_first * SEG ? H : T) + 32 * (size_t)s_first);
+  for (uint32_t s = s_first + 1; s <= s_last; s++) acc = pt_add_fast(acc, ld_pt(H + 32 * (size_t)s));
   st_pt(buckets + 32 * g, acc);
+}
+
+// warp-wide point sum: lane values -> lane 0 (shuffle tree, 5 additions deep)
+__device__ __forceinline__ Pt warp_sum_pt(Pt v) {
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    Pt o;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      o.X.w[k] = __shfl_down_sync(0xffffffffu, v.X.w[k], d);
+      o.Y.w[k] = __shfl_down_sync(0xffffffffu, v.Y.w[k], d);
+      o.Z.w[k] = __shfl_down_sync(0xffffffffu, v.Z.w[k], d);
+      o.T.w[k] = __shfl_down_sync(0xffffffffu, v.T.w[k], d);
+    }
+    v = pt_add_fast(v, o);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
+                                                        int nseg, int nb, const uint32_t* __restrict__ partH,
+                                                        const uint32_t* __restrict__ partT, uint32_t* __restrict__ buckets,
+                                                        const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
+  const uint32_t nheavy = *heavy_count;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t h = blockIdx.x * 4 + (threadIdx.x >> 5); h < nheavy; h += gridDim.x * 4) {
+    const uint32_t g = heavy_list[h];
+    const size_t wl = g / (uint32_t)nb;
+    const uint32_t o = offs[g], e = o + hist[g];
+    const uint32_t s_first = o / SEG, s_last = (e - 1) / SEG;
+    const uint32_t* H = partH + 32 * (wl * nseg);
+    const uint32_t* T = partT + 32 * (wl * nseg);
+    Pt acc = pt_identity_mont();
+    bool have = false;
+    for (uint32_t s = s_first + lane; s <= s_last; s += 32) {
+      Pt v = ld_pt(((s == s_first && o != s_first * SEG) ? T : H) + 32 * (size_t)s);
+      if (!have) { acc = v; have = true; } else acc = pt_add_fast(acc, v);
+    }
+    acc = warp_sum_pt(acc);
+    if (lane == 0) st_pt(buckets + 32 * (size_t)g, acc);
+  }
 }
 
 // ---- reduce level: chunks of CHUNK items -> (sum, weighted-from-zero sum) ----------------------------------------
@@ -293,7 +415,12 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o = 0;
     size_t o_cached = o; o = align_up(o + n * 128, 256);
     size_t o_digits = o; o = align_up(o + (size_t)nwl * n * 4, 256);
-    size_t o_sorted = o; o = align_up(o + (size_t)nwl * n * 4, 256);
+    const size_t n_pad = align_up(n, SEG);
+    const int nseg = (int)(n_pad / SEG);
+    size_t o_sorted = o; o = align_up(o + (size_t)nwl * n_pad * 4 + 256, 256);
+    size_t o_partH = o; o = align_up(o + (size_t)nwl * nseg * 128, 256);
+    size_t o_partT = o; o = align_up(o + (size_t)nwl * nseg * 128, 256);
+    size_t o_heavy = o; o = align_up(o + 256 + (size_t)nwl * nb * 4, 256);
     size_t o_hist = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_offs = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_cursor = o; o = align_up(o + (size_t)nwl * nb * 4, 256);
@@ -315,6 +442,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     int32_t *digits = (int32_t*)(ws + o_digits);
     uint32_t *sorted = (uint32_t*)(ws + o_sorted);
     uint32_t *hist = (uint32_t*)(ws + o_hist);
+    uint32_t *partH = (uint32_t*)(ws + o_partH);
+    uint32_t *partT = (uint32_t*)(ws + o_partT);
+    uint32_t *heavy_count = (uint32_t*)(ws + o_heavy);
+    uint32_t *heavy_list = heavy_count + 64;
     uint32_t *offs = (uint32_t*)(ws + o_offs);
     uint32_t *cursor = (uint32_t*)(ws + o_cursor);
     uint32_t *buckets = (uint32_t*)(ws + o_buckets);
@@ -325,16 +456,20 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     cudaStream_t st = ctx->stream;
 
     ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwl * nb * 4, st));
+    ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256, st));
     msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(points, cached, n); ctx->launches++;
     msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars, n, c, nwin, rank, nranks, digits, hist); ctx->launches++;
     msm_scan_kernel<<<nwl, 1024, 0, st>>>(hist, offs, cursor, nb); ctx->launches++;
     {
       size_t tot = n * (size_t)nwl;
-      msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, nwl, nb, cursor, sorted); ctx->launches++;
+      msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); ctx->launches++;
     }
     {
       size_t tot = (size_t)nwl * nb;
-      msm_accum_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(cached, sorted, offs, hist, n, nwl, nb, buckets); ctx->launches++;
+      size_t tseg = (size_t)nwl * nseg;
+      msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, sorted, offs, hist, n_pad, nseg, nwl, nb, buckets, partH, partT); ctx->launches++;
+      msm_fix_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(offs, hist, nseg, nwl, nb, partH, partT, buckets, heavy_count, heavy_list); ctx->launches++;
+      msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, nb, partH, partT, buckets, heavy_count, heavy_list); ctx->launches++;
     }
     // reduce levels
     const uint32_t *in = buckets; int n_in = nb;

@@ -1,0 +1,49 @@
+"""Run the 2^20-point MSM (BASELINE config 5) a few times on one GPU -- the target of ncu captures and quick timings."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dusk_zerocaf_b200 as zc
+from dusk_zerocaf_b200 import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1 << 20)
+ap.add_argument("--c", type=int, default=16)
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--nranks", type=int, default=1)
+ap.add_argument("--check", action="store_true")
+a = ap.parse_args()
+
+dev = torch.device("cuda", 0)
+st = torch.cuda.Stream()
+ctx = zc.Context(0, stream=st.cuda_stream)
+L = ctx._L
+n = a.n
+sc = torch.from_numpy(synth.synth_scalar(100, 0, n).view(np.int64)).to(dev)
+base = torch.from_numpy(np.tile(synth.BASEPOINT, (n, 1)).view(np.int64)).to(dev)
+P = torch.empty((n, 20), dtype=torch.int64, device=dev)
+ctx.check(L.zc_point_scalar_mul_batch_dev(ctx._h, base.data_ptr(), sc.data_ptr(), P.data_ptr(), n, 1))
+S = torch.from_numpy(synth.synth_scalar(102, 0, n).view(np.int64)).to(dev)
+out = torch.zeros(20, dtype=torch.int64, device=dev)
+ctx.sync()
+for it in range(a.iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    ctx.check(L.zc_msm_partial_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, a.c, a.rank, a.nranks, out.data_ptr()))
+    e1.record(st)
+    st.synchronize()
+    print(f"msm n={n} c={a.c} rank {a.rank}/{a.nranks}: {e0.elapsed_time(e1):.3f} ms", flush=True)
+if a.check:
+    from oracle import oracle as o
+    m = min(n, 2048)
+    got = torch.zeros(20, dtype=torch.int64, device=dev)
+    ctx.check(L.zc_msm_dev(ctx._h, P.data_ptr(), S.data_ptr(), m, a.c, got.data_ptr()))
+    ctx.sync()
+    want = o.msm_naive(P[:m].cpu().numpy().view(np.uint64), S[:m].cpu().numpy().view(np.uint64), threads=8)
+    print("check first", m, "points:", bool(o.pt_eq(got.cpu().numpy().view(np.uint64), want)))
