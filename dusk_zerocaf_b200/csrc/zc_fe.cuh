@@ -14,8 +14,11 @@
 // Both moduli have the shape  m = 2^k + c  with c < 2^125:  words 4,5,6 of m are zero and word 7 is a single
 // bit, so the "m * modulus" half of the Montgomery step costs 4 wide multiplies plus two shifts instead of 8.
 //
-// The multiply is a CIOS loop, fully unrolled, written as PTX mad.lo.cc / madc.hi.cc carry chains: even
-// and odd words of `a` feed two independent chains per row so the 64-bit products never overlap.
+// The Montgomery multiply is a CIOS loop, fully unrolled, written as PTX mad.lo.cc / madc.hi.cc carry chains that
+// ptxas fuses into IMAD.WIDE.U32[.X]; two accumulator arrays (even- and odd-aligned pairs) keep every 64-bit
+// product on an aligned register pair, so the loop has no register moves (measured 1.22x over a single-array CIOS).
+// Products of NORMAL-form operands (the ABI's element-wise mul / square) skip Montgomery altogether: a full 8x8
+// product followed by two folds with 2^K = -c (mod m), 112 wide multiplies instead of 2 x 96 + conversions.
 #pragma once
 #include <stdint.h>
 
@@ -130,70 +133,108 @@ __device__ __forceinline__ Fe fe_neg(const Fe& a) {   // field.rs:170-189 (0 - a
   return fe_sub<M>(z, a);
 }
 
-// ---- one CIOS row:  t = (t + a*bi + mq*m) / 2^32 -------------------------------------------------------
-// t has 9 live words on entry (t8 == 0) and 8 on exit (the caller renames t1..t8 -> t0..t7).
+// ---- Montgomery product, CIOS with split accumulators --------------------------------------------------------
+// The running value is kept in two register arrays whose 64-bit pairs never straddle:
+//     T = sum_k ev[k] 2^(32k)  +  sum_k od[k] 2^(32(k+1))
+// so every 32x32+64 multiply-add lands on an aligned register pair (IMAD.WIDE.U32[.X] with no register moves).  The
+// division by 2^32 after each row is absorbed by swapping the roles of the two arrays; the one realignment that swap
+// needs is done by 3-operand multiply-adds that read their addend two words further up (mont_row_next).
 template <class M>
-__device__ __forceinline__ void cios_row(uint32_t (&t)[9], const Fe& a, uint32_t bi) {
+__device__ __forceinline__ void mont_row_first(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(ev[j]), "=r"(ev[j + 1]) : "r"(a.w[j]), "r"(bi));
+    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(od[j]), "=r"(od[j + 1]) : "r"(a.w[j + 1]), "r"(bi));
+  }
+}
+// On entry `od` is the array that was word-aligned in the previous row: od[0] == 0 (reduced away), od[1] is a lone
+// word at the new offset 0 and od[2..7] sit at offsets 1..6; `ev` is aligned with the shifted value.
+template <class M>
+__device__ __forceinline__ void mont_row_next(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& a, uint32_t bi) {
   asm("{\n\t"
-      ".reg .u32 mq, lo, hi, z;\n\t"
-      // even words of a
-      "mad.lo.cc.u32   %0, %9,  %17, %0;\n\t"
-      "madc.hi.cc.u32  %1, %9,  %17, %1;\n\t"
-      "madc.lo.cc.u32  %2, %11, %17, %2;\n\t"
-      "madc.hi.cc.u32  %3, %11, %17, %3;\n\t"
-      "madc.lo.cc.u32  %4, %13, %17, %4;\n\t"
-      "madc.hi.cc.u32  %5, %13, %17, %5;\n\t"
-      "madc.lo.cc.u32  %6, %15, %17, %6;\n\t"
-      "madc.hi.cc.u32  %7, %15, %17, %7;\n\t"
-      "addc.u32        %8, %8, 0;\n\t"
-      // odd words of a
-      "mad.lo.cc.u32   %1, %10, %17, %1;\n\t"
-      "madc.hi.cc.u32  %2, %10, %17, %2;\n\t"
-      "madc.lo.cc.u32  %3, %12, %17, %3;\n\t"
-      "madc.hi.cc.u32  %4, %12, %17, %4;\n\t"
-      "madc.lo.cc.u32  %5, %14, %17, %5;\n\t"
-      "madc.hi.cc.u32  %6, %14, %17, %6;\n\t"
-      "madc.lo.cc.u32  %7, %16, %17, %7;\n\t"
-      "madc.hi.u32     %8, %16, %17, %8;\n\t"
-      // Montgomery quotient digit
-      "mul.lo.u32      mq, %0, %18;\n\t"
-      "shl.b32         lo, mq, %23;\n\t"
-      "shr.b32         hi, mq, %24;\n\t"
-      // + mq * m, even words (m4..m6 are zero, m7 is one bit -> shifts)
-      "mad.lo.cc.u32   z,  mq, %19, %0;\n\t"
-      "madc.hi.cc.u32  %1, mq, %19, %1;\n\t"
-      "madc.lo.cc.u32  %2, mq, %21, %2;\n\t"
-      "madc.hi.cc.u32  %3, mq, %21, %3;\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"                     // the lone word
+      "madc.lo.cc.u32  %8,  %17, %24, %10;\n\t"             // od[j], od[j+1] = a[j+1]*bi + od[j+2], od[j+3]
+      "madc.hi.cc.u32  %9,  %17, %24, %11;\n\t"
+      "madc.lo.cc.u32  %10, %19, %24, %12;\n\t"
+      "madc.hi.cc.u32  %11, %19, %24, %13;\n\t"
+      "madc.lo.cc.u32  %12, %21, %24, %14;\n\t"
+      "madc.hi.cc.u32  %13, %21, %24, %15;\n\t"
+      "madc.lo.cc.u32  %14, %23, %24, 0;\n\t"
+      "madc.hi.u32     %15, %23, %24, 0;\n\t"
+      "mad.lo.cc.u32   %0, %16, %24, %0;\n\t"               // ev pairs += a[even] * bi
+      "madc.hi.cc.u32  %1, %16, %24, %1;\n\t"
+      "madc.lo.cc.u32  %2, %18, %24, %2;\n\t"
+      "madc.hi.cc.u32  %3, %18, %24, %3;\n\t"
+      "madc.lo.cc.u32  %4, %20, %24, %4;\n\t"
+      "madc.hi.cc.u32  %5, %20, %24, %5;\n\t"
+      "madc.lo.cc.u32  %6, %22, %24, %6;\n\t"
+      "madc.hi.cc.u32  %7, %22, %24, %7;\n\t"
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]), "r"(bi));
+}
+// T += mq * m with mq = -T / m mod 2^32; afterwards ev[0] == 0.  Words 4..6 of m are zero and word 7 is one bit, so
+// the step costs 4 wide multiplies, one low multiply and two shifts.
+template <class M>
+__device__ __forceinline__ void mont_row_redc(uint32_t (&ev)[8], uint32_t (&od)[8]) {
+  asm("{\n\t"
+      ".reg .u32 mq, lo, hi;\n\t"
+      "mul.lo.u32      mq, %0, %16;\n\t"
+      "shl.b32         lo, mq, %21;\n\t"
+      "shr.b32         hi, mq, %22;\n\t"
+      "mad.lo.cc.u32   %8,  mq, %18, %8;\n\t"               // odd-aligned words of m: m1, m3, (m5 = 0), m7 = 1 << TOP
+      "madc.hi.cc.u32  %9,  mq, %18, %9;\n\t"
+      "madc.lo.cc.u32  %10, mq, %20, %10;\n\t"
+      "madc.hi.cc.u32  %11, mq, %20, %11;\n\t"
+      "addc.cc.u32     %12, %12, 0;\n\t"
+      "addc.cc.u32     %13, %13, 0;\n\t"
+      "addc.cc.u32     %14, %14, lo;\n\t"
+      "addc.u32        %15, %15, hi;\n\t"
+      "mad.lo.cc.u32   %0, mq, %17, %0;\n\t"                // even-aligned words of m: m0, m2, (m4 = m6 = 0)
+      "madc.hi.cc.u32  %1, mq, %17, %1;\n\t"
+      "madc.lo.cc.u32  %2, mq, %19, %2;\n\t"
+      "madc.hi.cc.u32  %3, mq, %19, %3;\n\t"
       "addc.cc.u32     %4, %4, 0;\n\t"
       "addc.cc.u32     %5, %5, 0;\n\t"
       "addc.cc.u32     %6, %6, 0;\n\t"
-      "addc.cc.u32     %7, %7, lo;\n\t"
-      "addc.u32        %8, %8, hi;\n\t"
-      // + mq * m, odd words
-      "mad.lo.cc.u32   %1, mq, %20, %1;\n\t"
-      "madc.hi.cc.u32  %2, mq, %20, %2;\n\t"
-      "madc.lo.cc.u32  %3, mq, %22, %3;\n\t"
-      "madc.hi.cc.u32  %4, mq, %22, %4;\n\t"
-      "addc.cc.u32     %5, %5, 0;\n\t"
-      "addc.cc.u32     %6, %6, 0;\n\t"
       "addc.cc.u32     %7, %7, 0;\n\t"
-      "addc.u32        %8, %8, 0;\n\t"
-      "}\n\t"
-      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
-      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
-        "r"(bi), "r"(M::NINV), "r"(M::M0), "r"(M::M1), "r"(M::M2), "r"(M::M3), "n"(M::TOP), "n"(32 - M::TOP));
-  t[0] = t[1]; t[1] = t[2]; t[2] = t[3]; t[3] = t[4]; t[4] = t[5]; t[5] = t[6]; t[6] = t[7]; t[7] = t[8]; t[8] = 0;
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(M::NINV), "r"(M::M0), "r"(M::M1), "r"(M::M2), "r"(M::M3), "n"(M::TOP), "n"(32 - M::TOP));
 }
 
 // ---- Montgomery product without the final subtraction: returns a*b/R + (< m), i.e. < 2m for a*b < R*m ----
 template <class M>
 __device__ __forceinline__ Fe mont_mul_lazy(const Fe& a, const Fe& b) {
-  uint32_t t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t ev[8], od[8];
+  mont_row_first<M>(ev, od, a, b.w[0]);
+  mont_row_redc<M>(ev, od);
 #pragma unroll
-  for (int i = 0; i < 8; i++) cios_row<M>(t, a, b.w[i]);
+  for (int i = 1; i < 8; i += 2) {
+    mont_row_next<M>(od, ev, a, b.w[i]);
+    mont_row_redc<M>(od, ev);
+    if (i + 1 < 8) {
+      mont_row_next<M>(ev, od, a, b.w[i + 1]);
+      mont_row_redc<M>(ev, od);
+    }
+  }
+  // the last row ran with od aligned (od[0] == 0) and ev one word up: result word k = ev[k] + od[k+1]
   Fe r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.w[i] = t[i];
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32    %7, %15, 0;\n\t"
+      : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+      : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
   return r;
 }
 
@@ -216,6 +257,230 @@ __device__ __forceinline__ Fe from_mont(const Fe& a) {
   Fe one{{1, 0, 0, 0, 0, 0, 0, 0}};
   return mont_mul<M>(a, one);
 }
+
+// ============================ products of NORMAL-form operands (no Montgomery) ============================
+// m = 2^K + c with c < 2^125 (4 words = M0..M3), so 2^K = -c (mod m).  For canonical a, b:
+//   T  = (a << SA)(b << SB) = 2^(256-K) a b                     SA + SB = 256 - K       64 wide multiplies
+//   H  = T >> 256 = floor(ab / 2^K),   Lo = (T mod 2^256) >> (256-K) = ab mod 2^K
+//   U  = c H  (< 2^380),   Uh = U >> K (< 2^128),   Ul = U mod 2^K                       32 wide multiplies
+//   V  = c Uh (< 2^253)                                                                   16 wide multiplies
+//   ab = Lo - Ul + V  (mod m),  in (-2^K, 2^(K+1)):  one conditional +m, one conditional -m.
+// This is the reference's Mul / Square (field.rs:250-262, 302-315; scalar.rs:247-283) as a value: canonical in,
+// canonical out, bit-identical limbs after repacking.
+
+// One row of a schoolbook product with split accumulators: X and Y are the two arrays (see mont_mul_lazy), X gets
+// a1,a3,a5,a7 (its top pair is fresh), Y gets a0,a2,a4,a6; the carry out of Y lands in X's fresh top word.
+#define ZC_WIDE_ROW8(X, XB, Y, YB, A, BI)                                                                          \
+  asm("{\n\t"                                                                                                      \
+      "mad.lo.cc.u32   %0, %17, %24, %0;\n\t"                                                                      \
+      "madc.hi.cc.u32  %1, %17, %24, %1;\n\t"                                                                      \
+      "madc.lo.cc.u32  %2, %19, %24, %2;\n\t"                                                                      \
+      "madc.hi.cc.u32  %3, %19, %24, %3;\n\t"                                                                      \
+      "madc.lo.cc.u32  %4, %21, %24, %4;\n\t"                                                                      \
+      "madc.hi.cc.u32  %5, %21, %24, %5;\n\t"                                                                      \
+      "madc.lo.cc.u32  %6, %23, %24, 0;\n\t"                                                                       \
+      "madc.hi.u32     %7, %23, %24, 0;\n\t"                                                                       \
+      "mad.lo.cc.u32   %8,  %16, %24, %8;\n\t"                                                                     \
+      "madc.hi.cc.u32  %9,  %16, %24, %9;\n\t"                                                                     \
+      "madc.lo.cc.u32  %10, %18, %24, %10;\n\t"                                                                    \
+      "madc.hi.cc.u32  %11, %18, %24, %11;\n\t"                                                                    \
+      "madc.lo.cc.u32  %12, %20, %24, %12;\n\t"                                                                    \
+      "madc.hi.cc.u32  %13, %20, %24, %13;\n\t"                                                                    \
+      "madc.lo.cc.u32  %14, %22, %24, %14;\n\t"                                                                    \
+      "madc.hi.cc.u32  %15, %22, %24, %15;\n\t"                                                                    \
+      "addc.u32        %7, %7, 0;\n\t"                                                                             \
+      "}"                                                                                                          \
+      : "+r"(X[XB]), "+r"(X[XB + 1]), "+r"(X[XB + 2]), "+r"(X[XB + 3]), "+r"(X[XB + 4]), "+r"(X[XB + 5]),          \
+        "=&r"(X[XB + 6]), "=&r"(X[XB + 7]),                                                                        \
+        "+r"(Y[YB]), "+r"(Y[YB + 1]), "+r"(Y[YB + 2]), "+r"(Y[YB + 3]), "+r"(Y[YB + 4]), "+r"(Y[YB + 5]),          \
+        "+r"(Y[YB + 6]), "+r"(Y[YB + 7])                                                                           \
+      : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(BI))
+
+#define ZC_WIDE_ROW8_FIRST(EV, OD, A, BI)                                                                          \
+  do {                                                                                                             \
+    _Pragma("unroll") for (int j_ = 0; j_ < 8; j_ += 2) {                                                          \
+      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(EV[j_]), "=r"(EV[j_ + 1]) : "r"(A[j_]), "r"(BI));      \
+      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(OD[j_]), "=r"(OD[j_ + 1]) : "r"(A[j_ + 1]), "r"(BI));  \
+    }                                                                                                              \
+  } while (0)
+
+// t[0..15] = a * b  (8 x 8 words, 64 wide multiplies)
+__device__ __forceinline__ void mul_wide_8x8(uint32_t (&t)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  uint32_t (&ev)[16] = t;
+  uint32_t od[14];
+  ZC_WIDE_ROW8_FIRST(ev, od, a, b[0]);
+  ZC_WIDE_ROW8(ev, 2, od, 0, a, b[1]);
+  ZC_WIDE_ROW8(od, 2, ev, 2, a, b[2]);
+  ZC_WIDE_ROW8(ev, 4, od, 2, a, b[3]);
+  ZC_WIDE_ROW8(od, 4, ev, 4, a, b[4]);
+  ZC_WIDE_ROW8(ev, 6, od, 4, a, b[5]);
+  ZC_WIDE_ROW8(od, 6, ev, 6, a, b[6]);
+  ZC_WIDE_ROW8(ev, 8, od, 6, a, b[7]);
+  // t = ev + (od << 32)
+  asm("add.cc.u32  %0, %0, %15;\n\t"
+      "addc.cc.u32 %1, %1, %16;\n\t"
+      "addc.cc.u32 %2, %2, %17;\n\t"
+      "addc.cc.u32 %3, %3, %18;\n\t"
+      "addc.cc.u32 %4, %4, %19;\n\t"
+      "addc.cc.u32 %5, %5, %20;\n\t"
+      "addc.cc.u32 %6, %6, %21;\n\t"
+      "addc.cc.u32 %7, %7, %22;\n\t"
+      "addc.cc.u32 %8, %8, %23;\n\t"
+      "addc.cc.u32 %9, %9, %24;\n\t"
+      "addc.cc.u32 %10, %10, %25;\n\t"
+      "addc.cc.u32 %11, %11, %26;\n\t"
+      "addc.cc.u32 %12, %12, %27;\n\t"
+      "addc.cc.u32 %13, %13, %28;\n\t"
+      "addc.u32    %14, %14, 0;\n\t"
+      : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]),
+        "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+      : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]),
+        "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]));
+}
+
+// u[0..11] = c * h   (c = the modulus' four low words, h 8 words; 32 wide multiplies)
+template <class M>
+__device__ __forceinline__ void mul_c_8(uint32_t (&u)[12], const uint32_t (&h)[8]) {
+  uint32_t (&ev)[12] = u;
+  uint32_t od[10];
+  const uint32_t c0 = M::M0, c1 = M::M1, c2 = M::M2, c3 = M::M3;
+  ZC_WIDE_ROW8_FIRST(ev, od, h, c0);
+  ZC_WIDE_ROW8(ev, 2, od, 0, h, c1);
+  ZC_WIDE_ROW8(od, 2, ev, 2, h, c2);
+  ZC_WIDE_ROW8(ev, 4, od, 2, h, c3);
+  asm("add.cc.u32  %0, %0, %11;\n\t"
+      "addc.cc.u32 %1, %1, %12;\n\t"
+      "addc.cc.u32 %2, %2, %13;\n\t"
+      "addc.cc.u32 %3, %3, %14;\n\t"
+      "addc.cc.u32 %4, %4, %15;\n\t"
+      "addc.cc.u32 %5, %5, %16;\n\t"
+      "addc.cc.u32 %6, %6, %17;\n\t"
+      "addc.cc.u32 %7, %7, %18;\n\t"
+      "addc.cc.u32 %8, %8, %19;\n\t"
+      "addc.cc.u32 %9, %9, %20;\n\t"
+      "addc.u32    %10, %10, 0;\n\t"
+      : "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]), "+r"(u[9]),
+        "+r"(u[10]), "+r"(u[11])
+      : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]),
+        "r"(od[9]));
+}
+
+// v[0..7] = c * g   (g 4 words; 16 wide multiplies).  Rows run over the words of g, the row operand is c.
+template <class M>
+__device__ __forceinline__ void mul_c_4(uint32_t (&v)[8], const uint32_t (&g)[4]) {
+  uint32_t (&ev)[8] = v;
+  uint32_t od[6];
+  const uint32_t c0 = M::M0, c1 = M::M1, c2 = M::M2, c3 = M::M3;
+  asm("mul.lo.u32 %0, %4, %8;\n\tmul.hi.u32 %1, %4, %8;\n\tmul.lo.u32 %2, %6, %8;\n\tmul.hi.u32 %3, %6, %8;"
+      : "=&r"(ev[0]), "=&r"(ev[1]), "=&r"(ev[2]), "=&r"(ev[3]) : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(g[0]));
+  asm("mul.lo.u32 %0, %5, %8;\n\tmul.hi.u32 %1, %5, %8;\n\tmul.lo.u32 %2, %7, %8;\n\tmul.hi.u32 %3, %7, %8;"
+      : "=&r"(od[0]), "=&r"(od[1]), "=&r"(od[2]), "=&r"(od[3]) : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(g[0]));
+#define ZC_WIDE_ROW4(X, XB, Y, YB, BI)                                                                             \
+  asm("{\n\t"                                                                                                      \
+      "mad.lo.cc.u32   %0, %9,  %12, %0;\n\t"                                                                      \
+      "madc.hi.cc.u32  %1, %9,  %12, %1;\n\t"                                                                      \
+      "madc.lo.cc.u32  %2, %11, %12, 0;\n\t"                                                                       \
+      "madc.hi.u32     %3, %11, %12, 0;\n\t"                                                                       \
+      "mad.lo.cc.u32   %4, %8,  %12, %4;\n\t"                                                                      \
+      "madc.hi.cc.u32  %5, %8,  %12, %5;\n\t"                                                                      \
+      "madc.lo.cc.u32  %6, %10, %12, %6;\n\t"                                                                      \
+      "madc.hi.cc.u32  %7, %10, %12, %7;\n\t"                                                                      \
+      "addc.u32        %3, %3, 0;\n\t"                                                                             \
+      "}"                                                                                                          \
+      : "+r"(X[XB]), "+r"(X[XB + 1]), "=&r"(X[XB + 2]), "=&r"(X[XB + 3]),                                          \
+        "+r"(Y[YB]), "+r"(Y[YB + 1]), "+r"(Y[YB + 2]), "+r"(Y[YB + 3])                                             \
+      : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(BI))
+  ZC_WIDE_ROW4(ev, 2, od, 0, g[1]);
+  ZC_WIDE_ROW4(od, 2, ev, 2, g[2]);
+  ZC_WIDE_ROW4(ev, 4, od, 2, g[3]);
+#undef ZC_WIDE_ROW4
+  asm("add.cc.u32  %0, %0, %7;\n\t"
+      "addc.cc.u32 %1, %1, %8;\n\t"
+      "addc.cc.u32 %2, %2, %9;\n\t"
+      "addc.cc.u32 %3, %3, %10;\n\t"
+      "addc.cc.u32 %4, %4, %11;\n\t"
+      "addc.cc.u32 %5, %5, %12;\n\t"
+      "addc.u32    %6, %6, 0;\n\t"
+      : "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+      : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]));
+}
+
+// K = bit length of the power of two in m; SA / SB = the two operand pre-shifts
+template <class M> struct Shape { static constexpr int K = 224 + M::TOP, S = 256 - K, SA = S / 2, SB = S - SA; };
+
+template <int S>
+__device__ __forceinline__ void shl_words(uint32_t (&r)[8], const Fe& a) {
+  r[0] = a.w[0] << S;
+#pragma unroll
+  for (int k = 1; k < 8; k++) r[k] = __funnelshift_l(a.w[k - 1], a.w[k], S);
+}
+
+// fold a 16-word product t = 2^(256-K) * x (x < m^2) to x mod m, canonical
+template <class M>
+__device__ __forceinline__ Fe fold_product(const uint32_t (&t)[16]) {
+  constexpr int S = Shape<M>::S, TOP = M::TOP;
+  uint32_t h[8], u[12], g[4], v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) h[k] = t[8 + k];
+  mul_c_8<M>(u, h);
+  // Uh = u >> K  (K = 224 + TOP)
+#pragma unroll
+  for (int k = 0; k < 4; k++) g[k] = __funnelshift_r(u[7 + k], u[8 + k], TOP);
+  mul_c_4<M>(v, g);
+  // Lo = t[0..7] >> S
+  Fe r;
+#pragma unroll
+  for (int k = 0; k < 7; k++) r.w[k] = __funnelshift_r(t[k], t[k + 1], S);
+  r.w[7] = t[7] >> S;
+  const uint32_t ul7 = u[7] & ((1u << TOP) - 1u);
+  uint32_t bw;
+  // r = Lo + V - Ul ; bw = all-ones when the result is negative
+  asm("add.cc.u32  %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "addc.cc.u32 %2, %2, %11;\n\t"
+      "addc.cc.u32 %3, %3, %12;\n\t"
+      "addc.cc.u32 %4, %4, %13;\n\t"
+      "addc.cc.u32 %5, %5, %14;\n\t"
+      "addc.cc.u32 %6, %6, %15;\n\t"
+      "addc.u32    %7, %7, %16;\n\t"
+      "sub.cc.u32  %0, %0, %17;\n\t"
+      "subc.cc.u32 %1, %1, %18;\n\t"
+      "subc.cc.u32 %2, %2, %19;\n\t"
+      "subc.cc.u32 %3, %3, %20;\n\t"
+      "subc.cc.u32 %4, %4, %21;\n\t"
+      "subc.cc.u32 %5, %5, %22;\n\t"
+      "subc.cc.u32 %6, %6, %23;\n\t"
+      "subc.cc.u32 %7, %7, %24;\n\t"
+      "subc.u32    %8, 0, 0;\n\t"
+      : "+r"(r.w[0]), "+r"(r.w[1]), "+r"(r.w[2]), "+r"(r.w[3]), "+r"(r.w[4]), "+r"(r.w[5]), "+r"(r.w[6]), "+r"(r.w[7]), "=r"(bw)
+      : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(ul7));
+  asm("add.cc.u32  %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t"
+      "addc.cc.u32 %6, %6, 0;\n\t"
+      "addc.u32    %7, %7, %12;\n\t"
+      : "+r"(r.w[0]), "+r"(r.w[1]), "+r"(r.w[2]), "+r"(r.w[3]), "+r"(r.w[4]), "+r"(r.w[5]), "+r"(r.w[6]), "+r"(r.w[7])
+      : "r"(bw & M::M0), "r"(bw & M::M1), "r"(bw & M::M2), "r"(bw & M::M3), "r"(bw & M::M7));
+  reduce_once<M>(r);
+  return r;
+}
+
+// a * b mod m for canonical NORMAL-form a, b (field.rs:250-262 / scalar.rs:247-258 as a value)
+template <class M>
+__device__ __forceinline__ Fe fe_mul_normal(const Fe& a, const Fe& b) {
+  uint32_t as[8], bs[8], t[16];
+  shl_words<Shape<M>::SA>(as, a);
+  shl_words<Shape<M>::SB>(bs, b);
+  mul_wide_8x8(t, as, bs);
+  return fold_product<M>(t);
+}
+// a^2 mod m (field.rs:302-315 / scalar.rs:272-283 as a value)
+template <class M>
+__device__ __forceinline__ Fe fe_sqr_normal(const Fe& a) { return fe_mul_normal<M>(a, a); }
 
 // ---- radix-2^52 limbs (the reference's [u64;5], field.rs:31-32) <-> 8 x u32 --------------------------
 __device__ __forceinline__ Fe fe_from_limbs52(uint64_t l0, uint64_t l1, uint64_t l2, uint64_t l3, uint64_t l4) {

@@ -15,7 +15,7 @@ constexpr int TPB = 256;
 enum FeOp { OP_MUL = 0, OP_SQUARE = 1, OP_ADD = 2, OP_SUB = 3, OP_NEG = 4 };
 
 // ---- K1: out[i] = a[i] (op) b[i]   (field.rs:191-315 / scalar.rs:184-283) -------------------------------
-// Normal-form operands: a*b = mont(mont(a, R^2), b) -- two Montgomery products, no final fix-up multiply.
+// Normal-form operands: full product + two folds with 2^K = -c (mod m)  (fe_mul_normal, zc_fe.cuh) -- no Montgomery.
 template <class M, int OP>
 __global__ void __launch_bounds__(TPB) fe_op_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
                                                     uint64_t* __restrict__ out, size_t n) {
@@ -25,9 +25,9 @@ __global__ void __launch_bounds__(TPB) fe_op_kernel(const uint64_t* __restrict__
   Fe r;
   if (OP == OP_MUL) {
     Fe y = fe_load52(b + 5 * i);
-    r = mont_mul<M>(to_mont<M>(x), y);
+    r = fe_mul_normal<M>(x, y);
   } else if (OP == OP_SQUARE) {
-    r = mont_mul<M>(to_mont<M>(x), x);
+    r = fe_sqr_normal<M>(x);
   } else if (OP == OP_ADD) {
     Fe y = fe_load52(b + 5 * i);
     r = fe_add<M>(x, y);
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(TPB) fe_op_kernel(const uint64_t* __restrict__
   fe_store52(out + 5 * i, r);
 }
 
-// ---- K1 fused (BASELINE config 2): prod = a*b, sq = a^2 sharing mont(a, R^2): 3 Montgomery products for 2 field ops
+// ---- K1 fused (BASELINE config 2): prod = a*b, sq = a^2 from one load of a
 template <class M>
 __global__ void __launch_bounds__(TPB) fe_mul_square_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
                                                             uint64_t* __restrict__ prod, uint64_t* __restrict__ sq, size_t n) {
@@ -48,9 +48,8 @@ __global__ void __launch_bounds__(TPB) fe_mul_square_kernel(const uint64_t* __re
   if (i >= n) return;
   Fe x = fe_load52(a + 5 * i);
   Fe y = fe_load52(b + 5 * i);
-  Fe xm = to_mont<M>(x);
-  fe_store52(prod + 5 * i, mont_mul<M>(xm, y));
-  fe_store52(sq + 5 * i, mont_mul<M>(xm, x));
+  fe_store52(prod + 5 * i, fe_mul_normal<M>(x, y));
+  fe_store52(sq + 5 * i, fe_sqr_normal<M>(x));
 }
 
 // ---- K2: point add / sub / double / neg on the ABI layout, limb-exact (edwards.rs:440-592) ----------------
