@@ -59,6 +59,8 @@ def lib():
     L.zc_ctx_sync.argtypes = [vp]
     L.zc_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
     L.zc_host_free.argtypes = [vp]
+    L.zc_host_register.argtypes = [vp, sz]
+    L.zc_host_unregister.argtypes = [vp]
     for mod in ("fe", "scalar"):
         for op in ("mul", "add", "sub"):
             for suf in ("", "_dev"):

@@ -8,6 +8,8 @@
 
 #include "../../include/zerocaf_b200.h"
 
+#define ZC_PIPE_MAX_CHUNKS 64
+
 struct zc_ctx {
   int device = 0;
   int sm_count = 148;
@@ -25,6 +27,12 @@ struct zc_ctx {
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;
   void *gather_buf = nullptr;   // nranks * 20 u64, device
+  // host-pointer entry points: copy-in / copy-out streams and per-chunk events (created on first use)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t pipe_ev[2 * ZC_PIPE_MAX_CHUNKS] = {};
+  // MSM: side stream for the window-scaling chain + events (created on first use)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 #define ZC_CUDA(ctx, call)                                                                       \

@@ -238,20 +238,66 @@ int32_t launch_pt(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* o
 
 constexpr size_t MAX_N = (size_t)1 << 31;
 
-// host-pointer wrapper: copy in (up to 2 inputs), run, copy out, synchronise
+// ---- host-pointer entry points: chunked, three-stage pipeline ----------------------------------------------------
+// H2D of chunk k+1 (copy-in stream), the kernel on chunk k (the context's stream) and D2H of chunk k-1 (copy-out
+// stream) overlap, so a PCIe-bound call costs max(H2D, D2H) instead of their sum.  Device staging is the grow-only
+// scratch of the context (whole arrays, so chunks never alias).  Pageable host memory still works (the copies then
+// serialise inside the driver); zc_host_alloc / zc_host_register give pinned memory and the full overlap.
+struct HostArr { const void* h_in; void* h_out; size_t stride; int slot; void* d; };
+
+constexpr size_t PIPE_CHUNK_BYTES = (size_t)16 << 20;
+
+int32_t pipe_setup(zc_ctx* ctx) {
+  if (ctx->copy_in) return ZC_OK;
+  ZC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  ZC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2 * ZC_PIPE_MAX_CHUNKS; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+  return ZC_OK;
+}
+
 template <class F>
-int32_t host_binary(zc_ctx* ctx, const void* a, size_t a_bytes, const void* b, size_t b_bytes, void* out, size_t out_bytes, F run) {
-  void *da = nullptr, *db = nullptr, *dout = nullptr;
+int32_t host_pipelined(zc_ctx* ctx, size_t n, HostArr* ins, int n_in, HostArr* outs, int n_out, F launch) {
   int32_t rc;
-  if ((rc = zc_scratch(ctx, 0, a_bytes, &da))) return rc;
-  if (b) { if ((rc = zc_scratch(ctx, 1, b_bytes, &db))) return rc; }
-  if ((rc = zc_scratch(ctx, 2, out_bytes, &dout))) return rc;
-  ZC_CUDA(ctx, cudaMemcpyAsync(da, a, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (b) ZC_CUDA(ctx, cudaMemcpyAsync(db, b, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = run(da, db, dout))) return rc;
-  ZC_CUDA(ctx, cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = pipe_setup(ctx))) return rc;
+  size_t max_stride = 1;
+  for (int i = 0; i < n_in; i++) { if ((rc = zc_scratch(ctx, ins[i].slot, n * ins[i].stride, &ins[i].d))) return rc; if (ins[i].stride > max_stride) max_stride = ins[i].stride; }
+  for (int i = 0; i < n_out; i++) { if ((rc = zc_scratch(ctx, outs[i].slot, n * outs[i].stride, &outs[i].d))) return rc; if (outs[i].stride > max_stride) max_stride = outs[i].stride; }
+  size_t chunk = PIPE_CHUNK_BYTES / max_stride;
+  if (chunk < 4096) chunk = 4096;
+  if ((n + chunk - 1) / chunk > ZC_PIPE_MAX_CHUNKS) chunk = (n + ZC_PIPE_MAX_CHUNKS - 1) / ZC_PIPE_MAX_CHUNKS;
+  // the copy streams must not run ahead of work already queued on the context's stream
+  ZC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[0], ctx->stream));
+  ZC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->pipe_ev[0], 0));
+  int k = 0;
+  for (size_t i0 = 0; i0 < n; i0 += chunk, k++) {
+    const size_t cnt = (n - i0 < chunk) ? n - i0 : chunk;
+    cudaEvent_t ev_in = ctx->pipe_ev[2 * k], ev_done = ctx->pipe_ev[2 * k + 1];
+    for (int i = 0; i < n_in; i++)
+      ZC_CUDA(ctx, cudaMemcpyAsync((char*)ins[i].d + i0 * ins[i].stride, (const char*)ins[i].h_in + i0 * ins[i].stride,
+                                   cnt * ins[i].stride, cudaMemcpyHostToDevice, ctx->copy_in));
+    ZC_CUDA(ctx, cudaEventRecord(ev_in, ctx->copy_in));
+    ZC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+    if ((rc = launch(i0, cnt))) return rc;
+    ZC_CUDA(ctx, cudaEventRecord(ev_done, ctx->stream));
+    ZC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_done, 0));
+    for (int i = 0; i < n_out; i++)
+      ZC_CUDA(ctx, cudaMemcpyAsync((char*)outs[i].h_out + i0 * outs[i].stride, (const char*)outs[i].d + i0 * outs[i].stride,
+                                   cnt * outs[i].stride, cudaMemcpyDeviceToHost, ctx->copy_out));
+  }
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
   ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ZC_OK;
+}
+
+// two inputs (b may be null) -> one output
+template <class F>
+int32_t host_binary(zc_ctx* ctx, size_t n, const void* a, size_t a_stride, const void* b, size_t b_stride, void* out, size_t out_stride, F run) {
+  HostArr ins[2] = {{a, nullptr, a_stride, 0, nullptr}, {b, nullptr, b_stride, 1, nullptr}};
+  HostArr outs[1] = {{nullptr, out, out_stride, 2, nullptr}};
+  return host_pipelined(ctx, n, ins, b ? 2 : 1, outs, 1, [&](size_t i0, size_t cnt) {
+    return run((const char*)ins[0].d + i0 * a_stride, b ? (const char*)ins[1].d + i0 * b_stride : nullptr,
+               (char*)outs[0].d + i0 * out_stride, cnt);
+  });
 }
 
 }  // namespace
@@ -297,6 +343,9 @@ int32_t zc_ctx_destroy(zc_ctx* ctx) {
   for (int i = 0; i < 6; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->msm_ws) cudaFree(ctx->msm_ws);
   if (ctx->gather_buf) cudaFree(ctx->gather_buf);
+  if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); for (int i = 0; i < 2 * ZC_PIPE_MAX_CHUNKS; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]); }
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ZC_OK;
@@ -320,6 +369,16 @@ int32_t zc_host_free(void* p) {
   cudaError_t e = cudaFreeHost(p);
   return e == cudaSuccess ? ZC_OK : -(int32_t)e;
 }
+int32_t zc_host_register(void* p, size_t bytes) {
+  if (!p) return ZC_ERR_NULL;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  return e == cudaSuccess ? ZC_OK : -(int32_t)e;
+}
+int32_t zc_host_unregister(void* p) {
+  if (!p) return ZC_ERR_NULL;
+  cudaError_t e = cudaHostUnregister(p);
+  return e == cudaSuccess ? ZC_OK : -(int32_t)e;
+}
 
 // ---- field / scalar element-wise ------------------------------------------------------------------------
 #define ZC_DEFINE_BIN(NAME, MOD, OP)                                                                              \
@@ -333,8 +392,8 @@ int32_t zc_host_free(void* p) {
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, a && b && out);                                                                             \
-    return host_binary(ctx, a, n * 40, b, n * 40, out, n * 40, [&](void* da, void* db, void* dout) {              \
-      return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, n);               \
+    return host_binary(ctx, n, a, 40, b, 40, out, 40, [&](const void* da, const void* db, void* dout, size_t m) { \
+      return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, m);               \
     });                                                                                                           \
   }
 #define ZC_DEFINE_UN(NAME, MOD, OP)                                                                               \
@@ -348,8 +407,8 @@ int32_t zc_host_free(void* p) {
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, a && out);                                                                                  \
-    return host_binary(ctx, a, n * 40, nullptr, 0, out, n * 40, [&](void* da, void*, void* dout) {                \
-      return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, n);                           \
+    return host_binary(ctx, n, a, 40, nullptr, 0, out, 40, [&](const void* da, const void*, void* dout, size_t m) { \
+      return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, m);                           \
     });                                                                                                           \
   }
 
@@ -377,19 +436,12 @@ int32_t zc_fe_mul_square_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b
   ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
   if (n == 0) return ZC_OK;
   ZC_CHECK_PTR(ctx, a && b && prod && sq);
-  void *da, *db, *dp, *ds;
-  int32_t rc;
-  if ((rc = zc_scratch(ctx, 0, n * 40, &da))) return rc;
-  if ((rc = zc_scratch(ctx, 1, n * 40, &db))) return rc;
-  if ((rc = zc_scratch(ctx, 2, n * 40, &dp))) return rc;
-  if ((rc = zc_scratch(ctx, 3, n * 40, &ds))) return rc;
-  ZC_CUDA(ctx, cudaMemcpyAsync(da, a, n * 40, cudaMemcpyHostToDevice, ctx->stream));
-  ZC_CUDA(ctx, cudaMemcpyAsync(db, b, n * 40, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = zc_fe_mul_square_batch_dev(ctx, (uint64_t*)da, (uint64_t*)db, (uint64_t*)dp, (uint64_t*)ds, n))) return rc;
-  ZC_CUDA(ctx, cudaMemcpyAsync(prod, dp, n * 40, cudaMemcpyDeviceToHost, ctx->stream));
-  ZC_CUDA(ctx, cudaMemcpyAsync(sq, ds, n * 40, cudaMemcpyDeviceToHost, ctx->stream));
-  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZC_OK;
+  HostArr ins[2] = {{a, nullptr, 40, 0, nullptr}, {b, nullptr, 40, 1, nullptr}};
+  HostArr outs[2] = {{nullptr, prod, 40, 2, nullptr}, {nullptr, sq, 40, 3, nullptr}};
+  return host_pipelined(ctx, n, ins, 2, outs, 2, [&](size_t i0, size_t cnt) {
+    return zc_fe_mul_square_batch_dev(ctx, (const uint64_t*)ins[0].d + 5 * i0, (const uint64_t*)ins[1].d + 5 * i0,
+                                      (uint64_t*)outs[0].d + 5 * i0, (uint64_t*)outs[1].d + 5 * i0, cnt);
+  });
 }
 
 // ---- points ----------------------------------------------------------------------------------------------
@@ -404,8 +456,8 @@ int32_t zc_fe_mul_square_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, p && q && out);                                                                             \
-    return host_binary(ctx, p, n * 160, q, n * 160, out, n * 160, [&](void* da, void* db, void* dout) {           \
-      return launch_pt<OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, n);                    \
+    return host_binary(ctx, n, p, 160, q, 160, out, 160, [&](const void* da, const void* db, void* dout, size_t m) { \
+      return launch_pt<OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, m);                    \
     });                                                                                                           \
   }
 #define ZC_DEFINE_PT_UN(NAME, OP)                                                                                 \
@@ -419,8 +471,8 @@ int32_t zc_fe_mul_square_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, p && out);                                                                                  \
-    return host_binary(ctx, p, n * 160, nullptr, 0, out, n * 160, [&](void* da, void*, void* dout) {              \
-      return launch_pt<OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, n);                                \
+    return host_binary(ctx, n, p, 160, nullptr, 0, out, 160, [&](const void* da, const void*, void* dout, size_t m) { \
+      return launch_pt<OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, m);                                \
     });                                                                                                           \
   }
 
@@ -442,8 +494,8 @@ int32_t zc_ristretto_eq_batch(zc_ctx* ctx, const uint64_t* p, const uint64_t* q,
   ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
   if (n == 0) return ZC_OK;
   ZC_CHECK_PTR(ctx, p && q && eq);
-  return host_binary(ctx, p, n * 160, q, n * 160, eq, n, [&](void* da, void* db, void* dout) {
-    return zc_ristretto_eq_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint8_t*)dout, n);
+  return host_binary(ctx, n, p, 160, q, 160, eq, 1, [&](const void* da, const void* db, void* dout, size_t m) {
+    return zc_ristretto_eq_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint8_t*)dout, m);
   });
 }
 
@@ -466,8 +518,8 @@ int32_t zc_point_scalar_mul_batch(zc_ctx* ctx, const uint64_t* points, const uin
   if (mode != ZC_SCALAR_MUL_STRICT && mode != ZC_SCALAR_MUL_FAST) return zc_fail(ctx, ZC_ERR_MODE, "unknown scalar-mul mode");
   if (n == 0) return ZC_OK;
   ZC_CHECK_PTR(ctx, points && scalars && out);
-  return host_binary(ctx, points, n * 160, scalars, n * 40, out, n * 160, [&](void* da, void* db, void* dout) {
-    return zc_point_scalar_mul_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, n, mode);
+  return host_binary(ctx, n, points, 160, scalars, 40, out, 160, [&](const void* da, const void* db, void* dout, size_t m) {
+    return zc_point_scalar_mul_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, m, mode);
   });
 }
 

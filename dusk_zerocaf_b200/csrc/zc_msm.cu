@@ -27,8 +27,7 @@ int32_t zc_nccl_allgather(zc_ctx *ctx, const void *send, void *recv, size_t byte
 namespace {
 
 constexpr int MAX_WINDOWS = 32;      // ceil(256 / 8)
-constexpr int CHUNK_LOG = 3;         // m = 8 buckets per chunk in the reduce levels
-constexpr int CHUNK = 1 << CHUNK_LOG;
+constexpr int MAX_GROUPS = 4;        // window groups processed top-down; the scaling chain of one group overlaps the next
 
 struct PtW { uint32_t w[32]; };      // packed point: 4 coordinates x 8 words (extended or cached, Montgomery form)
 
@@ -261,6 +260,12 @@ __global__ void __launch_bounds__(128) msm_fix_kernel(const uint32_t* __restrict
   st_pt(buckets + 32 * g, acc);
 }
 
+// Out-of-line point operations for the latency-bound tail kernels (reduce / heavy): one copy of the ~30 KB addition
+// body per kernel keeps them inside the instruction cache (inlined at every call site, msm_reduce1_kernel was 1 MB of
+// straight-line code and ran at ~8 cycles per instruction).
+__device__ __noinline__ Pt pt_add_ni(Pt p, Pt q) { return pt_add_fast(p, q); }
+__device__ __noinline__ Pt pt_double_ni(Pt p) { return pt_double_fast(p); }
+
 // warp-wide point sum: lane values -> lane 0 (shuffle tree, 5 additions deep)
 __device__ __forceinline__ Pt warp_sum_pt(Pt v) {
 #pragma unroll 1
@@ -273,7 +278,7 @@ __device__ __forceinline__ Pt warp_sum_pt(Pt v) {
       o.Z.w[k] = __shfl_down_sync(0xffffffffu, v.Z.w[k], d);
       o.T.w[k] = __shfl_down_sync(0xffffffffu, v.T.w[k], d);
     }
-    v = pt_add_fast(v, o);
+    v = pt_add_ni(v, o);
   }
   return v;
 }
@@ -295,90 +300,187 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restri
     bool have = false;
     for (uint32_t s = s_first + lane; s <= s_last; s += 32) {
       Pt v = ld_pt(((s == s_first && o != s_first * SEG) ? T : H) + 32 * (size_t)s);
-      if (!have) { acc = v; have = true; } else acc = pt_add_fast(acc, v);
+      if (!have) { acc = v; have = true; } else acc = pt_add_ni(acc, v);
     }
     acc = warp_sum_pt(acc);
     if (lane == 0) st_pt(buckets + 32 * (size_t)g, acc);
   }
 }
 
-// ---- reduce level: chunks of CHUNK items -> (sum, weighted-from-zero sum) ----------------------------------------
-// For chunk items I_0..I_{m-1}:  sums = sum I_j,  acc0 = sum j * I_j   (descending running sum)
-__global__ void __launch_bounds__(128) msm_chunk_kernel(const uint32_t* __restrict__ in, int n_in, int nwl,
-                                                        uint32_t* __restrict__ sums, uint32_t* __restrict__ acc0) {
-  const int n_out = (n_in + CHUNK - 1) / CHUNK;
-  size_t g = (size_t)blockIdx.x * 128 + threadIdx.x;
-  if (g >= (size_t)nwl * n_out) return;
-  size_t wl = g / n_out, t = g - wl * n_out;
-  const uint32_t* base = in + 32 * (wl * n_in);
-  int lo = (int)t * CHUNK;
-  int hi = min(lo + CHUNK, n_in);
-  Pt run = ld_pt(base + 32 * (size_t)(hi - 1));
-  Pt acc = run;
-  if (hi - 1 == lo) acc = pt_identity_mont();
-  for (int k = hi - 2; k >= lo; k--) {
-    run = pt_add_fast(run, ld_pt(base + 32 * (size_t)k));
-    if (k > lo) acc = pt_add_fast(acc, run);
+// lane-to-lane copies of a field element / point
+__device__ __forceinline__ Fe shfl_fe(const Fe& a, int src) {
+  Fe r;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.w[k] = __shfl_sync(0xffffffffu, a.w[k], src);
+  return r;
+}
+__device__ __forceinline__ Pt shfl_down_pt(const Pt& v, int d) {
+  Pt o;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    o.X.w[k] = __shfl_down_sync(0xffffffffu, v.X.w[k], d);
+    o.Y.w[k] = __shfl_down_sync(0xffffffffu, v.Y.w[k], d);
+    o.Z.w[k] = __shfl_down_sync(0xffffffffu, v.Z.w[k], d);
+    o.T.w[k] = __shfl_down_sync(0xffffffffu, v.T.w[k], d);
   }
-  // acc = sum_{k>lo} (k-lo) I_k  (for hi-1 > lo the loop added run for k = hi-2 .. lo+1 on top of the initial I_{hi-1})
-  st_pt(sums + 32 * g, run);
-  st_pt(acc0 + 32 * g, acc);
+  return o;
 }
 
-// ---- plain sum of n items per window (one block per window) ---------------------------------------------------------
-constexpr int SUM_TPB = 256;
-__global__ void __launch_bounds__(SUM_TPB) msm_sum_kernel(const uint32_t* __restrict__ in, int n_in, uint32_t* __restrict__ out, int out_stride, int out_slot) {
-  __shared__ uint32_t sm[SUM_TPB * 32];
-  const int wl = blockIdx.x;
-  const uint32_t* base = in + 32 * ((size_t)wl * n_in);
-  Pt acc = pt_identity_mont();
-  bool have = false;
-  for (int k = threadIdx.x; k < n_in; k += SUM_TPB) {
-    Pt v = ld_pt(base + 32 * (size_t)k);
-    if (!have) { acc = v; have = true; } else acc = pt_add_fast(acc, v);
-  }
-  st_pt(sm + 32 * threadIdx.x, acc);
-  __syncthreads();
-  for (int d = SUM_TPB / 2; d >= 1; d >>= 1) {
-    if (threadIdx.x < d) {
-      Pt a = ld_pt(sm + 32 * threadIdx.x);
-      Pt b = ld_pt(sm + 32 * (threadIdx.x + d));
-      st_pt(sm + 32 * threadIdx.x, pt_add_fast(a, b));
+// ---- bucket reduction  W = sum_k (k+1) B_k,  two warp-cooperative levels ------------------------------------------
+// A warp owns RCH = 32 * RQ consecutive items.  Lane l walks its RQ items with the running-sum trick
+//   c_l = sum_j I_j,   a_l = sum_j j I_j          (2 RQ - 1 additions, serial)
+// then the warp takes a suffix scan S_l = sum_{i >= l} c_i (5 shuffle steps) and one tree sum:
+//   sum_k (k - base) I_k = sum_l (a_l + RQ * l * c_l) = sum_l a_l + RQ * sum_{l >= 1} S_l.
+// Depth per level ~ 2 RQ + 14 additions instead of the 5 chunk + 5 tree launches this replaces.
+constexpr int RQ = 8;
+constexpr int RCH = 32 * RQ;      // 256 buckets per warp at level 0
+
+template <int Q, bool WITH_PLAIN>
+__device__ __forceinline__ void warp_weighted(const uint32_t* __restrict__ items, const uint32_t* __restrict__ plain,
+                                              int n_items, int lane, Pt& total, Pt& weighted, Pt& plain_sum) {
+  // lane's items: indices lane*Q .. lane*Q+Q-1  (identity beyond n_items)
+  const int lo = lane * Q;
+  Pt run = pt_identity_mont(), acc = pt_identity_mont(), pl = pt_identity_mont();
+#pragma unroll 1
+  for (int j = Q - 1; j >= 0; j--) {
+    const int k = lo + j;
+    if (k < n_items) {
+      run = pt_add_ni(run, ld_pt(items + 32 * (size_t)k));
+      if (WITH_PLAIN) pl = pt_add_ni(pl, ld_pt(plain + 32 * (size_t)k));
     }
-    __syncthreads();
+    if (j > 0) acc = pt_add_ni(acc, run);
   }
-  if (threadIdx.x == 0) st_pt(out + 32 * ((size_t)wl * out_stride + out_slot), ld_pt(sm));
+  // suffix scan of run over lanes
+  Pt S = run;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Pt o = shfl_down_pt(S, d);
+    Pt t = pt_add_ni(S, o);
+    if (lane + d < 32) S = t;
+  }
+  // z = Q * (lane >= 1 ? S : 0) + acc
+  Pt z = (lane >= 1) ? S : pt_identity_mont();
+#pragma unroll
+  for (int q = Q; q > 1; q >>= 1) z = pt_double_ni(z);
+  z = pt_add_ni(z, acc);
+  weighted = warp_sum_pt(z);
+  total = S;                 // valid on lane 0
+  if (WITH_PLAIN) plain_sum = warp_sum_pt(pl);
 }
 
-// ---- combine: per window Horner over the levels, then Horner over the windows with 2^c scalings -------------------
-// level_sums[wl][l] (l = 0..nlev-1) = S_l = sum_t acc0^(l)_t ;  level_sums[wl][nlev] = Total = sum of all buckets.
-// window sum  W = Total + sum_l m^l S_l.   partial = sum_{local w} 2^(c w) W_w.
-__global__ void msm_combine_kernel(const uint32_t* __restrict__ level_sums, int nlev, int nwl, int c, int nwin,
-                                   int rank, int nranks, uint64_t* __restrict__ out52, uint32_t* __restrict__ wsum) {
-  const int wl = threadIdx.x;
-  if (wl < nwl) {
-    const uint32_t* ls = level_sums + 32 * ((size_t)wl * (nlev + 1));
-    Pt r = ld_pt(ls + 32 * (size_t)(nlev - 1));
-    for (int l = nlev - 2; l >= 0; l--) {
-      for (int j = 0; j < CHUNK_LOG; j++) r = pt_double_fast(r);
-      r = pt_add_fast(r, ld_pt(ls + 32 * (size_t)l));
-    }
-    r = pt_add_fast(r, ld_pt(ls + 32 * (size_t)nlev));
-    st_pt(wsum + 32 * wl, r);
+// level 0: one warp per chunk of RCH buckets -> chunk sum C_t and chunk-local weighted sum Wt_t = sum (k - base) B_k
+__global__ void __launch_bounds__(128) msm_reduce0_kernel(const uint32_t* __restrict__ buckets, int nb, int nchunk, int nwl,
+                                                          uint32_t* __restrict__ csum, uint32_t* __restrict__ wloc) {
+  const int lane = threadIdx.x & 31;
+  const size_t g = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (g >= (size_t)nwl * nchunk) return;
+  const size_t wl = g / nchunk;
+  const int t = (int)(g - wl * nchunk);
+  const int base = t * RCH;
+  Pt total, weighted, unused;
+  warp_weighted<RQ, false>(buckets + 32 * (wl * nb + base), nullptr, min(RCH, nb - base), lane, total, weighted, unused);
+  if (lane == 0) { st_pt(csum + 32 * g, total); st_pt(wloc + 32 * g, weighted); }
+}
+
+// level 1: one warp per window.  W = sum_t [ Wt_t + (t RCH + 1) C_t ] = sum_t Wt_t + sum_t C_t + RCH * sum_t t C_t
+template <int Q1>
+__device__ __forceinline__ Pt reduce1_body(const uint32_t* __restrict__ csum, const uint32_t* __restrict__ wloc, int nchunk, int lane) {
+  Pt total, weighted, plain;
+  warp_weighted<Q1, true>(csum, wloc, nchunk, lane, total, weighted, plain);
+#pragma unroll 1
+  for (int q = RCH; q > 1; q >>= 1) weighted = pt_double_ni(weighted);
+  return pt_add_ni(pt_add_ni(weighted, total), plain);   // valid on lane 0
+}
+__global__ void __launch_bounds__(32) msm_reduce1_kernel(const uint32_t* __restrict__ csum, const uint32_t* __restrict__ wloc,
+                                                         int nchunk, uint32_t* __restrict__ wsum) {
+  const int lane = threadIdx.x;
+  const size_t wl = blockIdx.x;
+  const uint32_t* c = csum + 32 * (wl * nchunk);
+  const uint32_t* w = wloc + 32 * (wl * nchunk);
+  Pt r;
+  if (nchunk <= 32) r = reduce1_body<1>(c, w, nchunk, lane);
+  else if (nchunk <= 64) r = reduce1_body<2>(c, w, nchunk, lane);
+  else r = reduce1_body<4>(c, w, nchunk, lane);
+  if (lane == 0) st_pt(wsum + 32 * wl, r);
+}
+
+// ---- window chain: acc = 2^(c w) - weighted sum of this rank's window sums, four lanes per point operation ----------
+// Lane q = lane & 3 holds coordinate q (X, Y, Z, T) of the running point; the four independent field multiplications
+// of each of the two stages of a doubling / addition run on the four lanes, the operands travel by shuffle.  This
+// turns the strictly serial tail (c doublings per window) from ~8 dependent multiplications per operation into 2.
+__device__ __forceinline__ Fe quad_stage2(const Fe& E, const Fe& F, const Fe& G, const Fe& H, int q) {
+  typedef ModP M;
+  // X3 = E F, Y3 = G H, Z3 = F G, T3 = E H
+  Fe u, v;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    u.w[k] = (q == 0 || q == 3) ? E.w[k] : (q == 1 ? G.w[k] : F.w[k]);
+    v.w[k] = (q == 0) ? F.w[k] : (q == 2 ? G.w[k] : H.w[k]);
   }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  Pt acc = pt_identity_mont();
-  bool started = false;
-  for (int w = nwin - 1; w >= 0; w--) {
-    if (started) for (int j = 0; j < c; j++) acc = pt_double_fast(acc);
-    if (w % nranks == rank) {
-      Pt ww = ld_pt(wsum + 32 * (size_t)(w / nranks));
-      if (started) acc = pt_add_fast(acc, ww); else { acc = ww; started = true; }
+  return mont_mul<M>(u, v);
+}
+__device__ __forceinline__ Fe quad_double(const Fe& c, int q, int qbase) {
+  typedef ModP M;
+  Fe x = shfl_fe(c, qbase), y = shfl_fe(c, qbase + 1);
+  Fe in = c;
+  if (q == 3) in = fe_add<M>(x, y);
+  Fe s = mont_mul<M>(in, in);                                  // A, B, ZZ, (X+Y)^2 on lanes 0..3
+  Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), ZZ = shfl_fe(s, qbase + 2), SS = shfl_fe(s, qbase + 3);
+  Fe C = fe_add<M>(ZZ, ZZ);
+  Fe D = fe_neg<M>(A);
+  Fe E = fe_sub<M>(fe_sub<M>(SS, A), B);
+  Fe G = fe_add<M>(D, B);
+  Fe F = fe_sub<M>(G, C);
+  Fe H = fe_sub<M>(D, B);
+  return quad_stage2(E, F, G, H, q);
+}
+// c (distributed over the quad) += the full point p (every lane holds all of p)
+__device__ __forceinline__ Fe quad_add(const Fe& c, const Pt& p, int q, int qbase) {
+  typedef ModP M;
+  Fe x1 = shfl_fe(c, qbase), y1 = shfl_fe(c, qbase + 1);
+  Fe u, v;
+  if (q == 0)      { u = fe_sub<M>(y1, x1); v = fe_sub<M>(p.Y, p.X); }
+  else if (q == 1) { u = fe_add<M>(y1, x1); v = fe_add<M>(p.Y, p.X); }
+  else if (q == 2) { u = c;                 v = fe_add<M>(p.Z, p.Z); }
+  else             { u = c;                 v = mont_mul<M>(p.T, D2_MONT()); }
+  Fe s = mont_mul<M>(u, v);                                    // A, B, D = 2 Z1 Z2, C = T1 2d T2
+  Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), D = shfl_fe(s, qbase + 2), C = shfl_fe(s, qbase + 3);
+  Fe E = fe_sub<M>(B, A);
+  Fe F = fe_sub<M>(D, C);
+  Fe G = fe_add<M>(D, C);
+  Fe H = fe_add<M>(B, A);
+  return quad_stage2(E, F, G, H, q);
+}
+
+// One warp.  acc (in/out, extended Montgomery words) is the running sum already scaled to this group's top window.
+//   for i in 0..ng-1:  if (i > 0) acc = 2^gap_in acc;   acc += wsum[i]       (group windows in descending order)
+//   acc = 2^gap_post acc
+// first != 0: acc starts as the identity.  out52 != nullptr: also store the result in the ABI layout.
+__global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ wsum, int ng, int wsum_step, int first,
+                                                       int gap_in, int gap_post, uint32_t* __restrict__ acc_io,
+                                                       uint64_t* __restrict__ out52) {
+  const int lane = threadIdx.x;
+  const int q = lane & 3, qbase = lane & ~3;
+  Pt a0 = first ? pt_identity_mont() : ld_pt(acc_io);
+  Fe c = (q == 0) ? a0.X : (q == 1 ? a0.Y : (q == 2 ? a0.Z : a0.T));
+#pragma unroll 1
+  for (int i = 0; i < ng; i++) {
+    if (i > 0) {
+#pragma unroll 1
+      for (int j = 0; j < gap_in; j++) c = quad_double(c, q, qbase);
     }
+    Pt w = ld_pt(wsum + 32 * ((ptrdiff_t)i * wsum_step));
+    c = quad_add(c, w, q, qbase);
   }
-  // Montgomery-form words read as normal form are the same point scaled by R: store them directly.
-  pt_store52(out52, acc);
+#pragma unroll 1
+  for (int j = 0; j < gap_post; j++) c = quad_double(c, q, qbase);
+  Pt r;
+  r.X = shfl_fe(c, 0); r.Y = shfl_fe(c, 1); r.Z = shfl_fe(c, 2); r.T = shfl_fe(c, 3);
+  if (lane == 0) {
+    st_pt(acc_io, r);
+    // Montgomery-form words read as normal form are the same point scaled by R: store them directly.
+    if (out52) pt_store52(out52, r);
+  }
 }
 
 }  // namespace
@@ -395,10 +497,6 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
   const int nb = 1 << (c - 1);
   int nwl = 0;
   for (int w = 0; w < nwin; w++) if (w % nranks == rank) nwl++;
-
-  // level geometry
-  int lev_n[16]; int nlev = 0;
-  { int cur = nb; while (cur > 1) { cur = (cur + CHUNK - 1) / CHUNK; lev_n[nlev++] = cur; } }
 
   uint64_t *partial = exchange ? nullptr : out_point_dev;
   if (exchange) {
@@ -420,16 +518,15 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o_sorted = o; o = align_up(o + (size_t)nwl * n_pad * 4 + 256, 256);
     size_t o_partH = o; o = align_up(o + (size_t)nwl * nseg * 128, 256);
     size_t o_partT = o; o = align_up(o + (size_t)nwl * nseg * 128, 256);
-    size_t o_heavy = o; o = align_up(o + 256 + (size_t)nwl * nb * 4, 256);
+    size_t o_heavy = o; o = align_up(o + 256 * MAX_GROUPS + (size_t)nwl * nb * 4, 256);
     size_t o_hist = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_offs = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_cursor = o; o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_buckets = o; o = align_up(o + (size_t)nwl * nb * 128, 256);
-    size_t o_sums[2]; size_t o_acc0;
-    o_sums[0] = o; o = align_up(o + (size_t)nwl * lev_n[0] * 128, 256);
-    o_sums[1] = o; o = align_up(o + (size_t)nwl * lev_n[0] * 128, 256);
-    o_acc0 = o;    o = align_up(o + (size_t)nwl * lev_n[0] * 128, 256);
-    size_t o_lsum = o; o = align_up(o + (size_t)nwl * (nlev + 1) * 128, 256);
+    const int nchunk = (nb + RCH - 1) / RCH;
+    size_t o_csum = o; o = align_up(o + (size_t)nwl * nchunk * 128, 256);
+    size_t o_wloc = o; o = align_up(o + (size_t)nwl * nchunk * 128, 256);
+    size_t o_acc = o;  o = align_up(o + 128, 256);
     size_t o_wsum = o; o = align_up(o + (size_t)nwl * 128, 256);
     if (o > ctx->msm_ws_bytes) {
       if (ctx->msm_ws) ZC_CUDA(ctx, cudaFree(ctx->msm_ws));
@@ -444,19 +541,24 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     uint32_t *hist = (uint32_t*)(ws + o_hist);
     uint32_t *partH = (uint32_t*)(ws + o_partH);
     uint32_t *partT = (uint32_t*)(ws + o_partT);
-    uint32_t *heavy_count = (uint32_t*)(ws + o_heavy);
-    uint32_t *heavy_list = heavy_count + 64;
+    uint32_t *heavy_count = (uint32_t*)(ws + o_heavy);          // one counter per group, 256 B apart
+    uint32_t *heavy_list = heavy_count + 64 * MAX_GROUPS;
     uint32_t *offs = (uint32_t*)(ws + o_offs);
     uint32_t *cursor = (uint32_t*)(ws + o_cursor);
     uint32_t *buckets = (uint32_t*)(ws + o_buckets);
-    uint32_t *sums[2] = {(uint32_t*)(ws + o_sums[0]), (uint32_t*)(ws + o_sums[1])};
-    uint32_t *acc0 = (uint32_t*)(ws + o_acc0);
-    uint32_t *lsum = (uint32_t*)(ws + o_lsum);
+    uint32_t *csum = (uint32_t*)(ws + o_csum);
+    uint32_t *wloc = (uint32_t*)(ws + o_wloc);
+    uint32_t *acc = (uint32_t*)(ws + o_acc);
     uint32_t *wsum = (uint32_t*)(ws + o_wsum);
     cudaStream_t st = ctx->stream;
+    if (!ctx->side_stream) {
+      ZC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < MAX_GROUPS + 1; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    }
+    cudaStream_t side = ctx->side_stream;
 
     ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwl * nb * 4, st));
-    ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256, st));
+    ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
     msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(points, cached, n); ctx->launches++;
     msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars, n, c, nwin, rank, nranks, digits, hist); ctx->launches++;
     msm_scan_kernel<<<nwl, 1024, 0, st>>>(hist, offs, cursor, nb); ctx->launches++;
@@ -464,25 +566,35 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       size_t tot = n * (size_t)nwl;
       msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); ctx->launches++;
     }
-    {
-      size_t tot = (size_t)nwl * nb;
-      size_t tseg = (size_t)nwl * nseg;
-      msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, sorted, offs, hist, n_pad, nseg, nwl, nb, buckets, partH, partT); ctx->launches++;
-      msm_fix_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(offs, hist, nseg, nwl, nb, partH, partT, buckets, heavy_count, heavy_list); ctx->launches++;
-      msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, nb, partH, partT, buckets, heavy_count, heavy_list); ctx->launches++;
+    // Window groups, top-down.  Local window wl is global window rank + nranks * wl.  After a group's buckets are
+    // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
+    // next group's top window (or, after the last group, by 2^(c * rank)) while the main stream accumulates the next group.
+    const int ngroups = nwl < MAX_GROUPS ? nwl : MAX_GROUPS;
+    int hi = nwl;
+    for (int g = 0; g < ngroups; g++) {
+      const int gsz = (hi + (ngroups - g) - 1) / (ngroups - g);
+      const int lo = hi - gsz;
+      const size_t tot = (size_t)gsz * nb;
+      const size_t tseg = (size_t)gsz * nseg;
+      const uint32_t *g_sorted = sorted + (size_t)lo * n_pad, *g_offs = offs + (size_t)lo * nb, *g_hist = hist + (size_t)lo * nb;
+      uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg), *g_partT = partT + 32 * ((size_t)lo * nseg);
+      uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
+      msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, gsz, nb, g_buckets, g_partH, g_partT); ctx->launches++;
+      // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
+      // stream, under the next group's accumulation
+      ZC_CUDA(ctx, cudaEventRecord(ctx->ev[g], st));
+      ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[g], 0));
+      msm_fix_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, side>>>(g_offs, g_hist, nseg, gsz, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); ctx->launches++;
+      msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); ctx->launches++;
+      msm_reduce0_kernel<<<(unsigned)(((size_t)gsz * nchunk + 3) / 4), 128, 0, side>>>(g_buckets, nb, nchunk, gsz, csum + 32 * ((size_t)lo * nchunk), wloc + 32 * ((size_t)lo * nchunk)); ctx->launches++;
+      msm_reduce1_kernel<<<gsz, 32, 0, side>>>(csum + 32 * ((size_t)lo * nchunk), wloc + 32 * ((size_t)lo * nchunk), nchunk, wsum + 32 * (size_t)lo); ctx->launches++;
+      const bool last = (g == ngroups - 1);
+      msm_chain_kernel<<<1, 32, 0, side>>>(wsum + 32 * (size_t)(hi - 1), gsz, -1, g == 0 ? 1 : 0, c * nranks, last ? c * rank : c * nranks,
+                                           acc, last ? partial : nullptr); ctx->launches++;
+      hi = lo;
     }
-    // reduce levels
-    const uint32_t *in = buckets; int n_in = nb;
-    for (int l = 0; l < nlev; l++) {
-      int n_out = lev_n[l];
-      size_t tot = (size_t)nwl * n_out;
-      msm_chunk_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(in, n_in, nwl, sums[l & 1], acc0); ctx->launches++;
-      msm_sum_kernel<<<nwl, SUM_TPB, 0, st>>>(acc0, n_out, lsum, nlev + 1, l); ctx->launches++;
-      in = sums[l & 1]; n_in = n_out;
-    }
-    // Total = the single item left at the top level
-    msm_sum_kernel<<<nwl, SUM_TPB, 0, st>>>(in, n_in, lsum, nlev + 1, nlev); ctx->launches++;
-    msm_combine_kernel<<<1, 32, 0, st>>>(lsum, nlev, nwl, c, nwin, rank, nranks, partial, wsum); ctx->launches++;
+    ZC_CUDA(ctx, cudaEventRecord(ctx->ev[MAX_GROUPS], side));
+    ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[MAX_GROUPS], 0));
     ZC_CUDA(ctx, cudaGetLastError());
   }
 

@@ -19,7 +19,8 @@
  * Nothing aborts or throws across the boundary (the reference panics instead: scalar.rs:465, field.rs:285).
  * There is no CPU fallback: without a CUDA device zc_ctx_create fails with a negative status.
  *
- * Plain functions take HOST pointers (copy in, compute, copy out, synchronous).  `_dev` twins take DEVICE pointers,
+ * Plain functions take HOST pointers (synchronous; internally a chunked pipeline: H2D of chunk k+1, the kernel on chunk k
+ * and D2H of chunk k-1 overlap when the host memory is pinned -- zc_host_alloc / zc_host_register).  `_dev` twins take DEVICE pointers,
  * enqueue on the context's stream and return without synchronising (zc_ctx_sync waits).  `out` may alias an input
  * exactly (in place) but must not partially overlap.  A context is bound to one device and one stream and is not
  * thread-safe; distinct contexts are independent.
@@ -58,6 +59,10 @@ uint64_t zc_ctx_launch_count(zc_ctx *ctx);
 /* pinned host memory for callers that want full-speed copies */
 int32_t zc_host_alloc(size_t bytes, void **out);
 int32_t zc_host_free(void *p);
+/* pin / unpin memory the caller already owns (e.g. a Rust Vec<FieldElement>) so the host-pointer entry points can
+ * overlap their H2D and D2H copies with the kernels */
+int32_t zc_host_register(void *p, size_t bytes);
+int32_t zc_host_unregister(void *p);
 
 /* ---- FieldElement batch ops: out[i] = a[i] (op) b[i] mod p ------------------------------------------------ */
 /* replaces Mul  field.rs:250-275 */
