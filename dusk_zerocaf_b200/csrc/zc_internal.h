@@ -10,6 +10,14 @@
 
 #define ZC_PIPE_MAX_CHUNKS 64
 
+// arguments an instantiated MSM graph was recorded with (zc_msm.cu)
+struct zc_msm_key {
+  const void *points, *scalars;
+  size_t n;
+  int32_t c, rank, nranks, pad;
+  const void *partial, *ws;
+};
+
 struct zc_ctx {
   int device = 0;
   int sm_count = 148;
@@ -30,9 +38,12 @@ struct zc_ctx {
   // host-pointer entry points: copy-in / copy-out streams and per-chunk events (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t pipe_ev[2 * ZC_PIPE_MAX_CHUNKS] = {};
+  void *msm_graph_exec = nullptr;   // cudaGraphExec_t of the last MSM configuration
+  zc_msm_key msm_key = {};
+  uint64_t msm_graph_launches = 0;
   // MSM: side stream for the window-scaling chain + events (created on first use)
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t side_stream = nullptr, chain_stream = nullptr;
+  cudaEvent_t ev[16] = {};
 };
 
 #define ZC_CUDA(ctx, call)                                                                       \

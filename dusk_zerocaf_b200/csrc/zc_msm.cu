@@ -78,65 +78,100 @@ __global__ void __launch_bounds__(256) msm_prep_kernel(const uint64_t* __restric
 
 // ---- digits + histogram ----------------------------------------------------------------------------------------
 // digit d_w in [-2^(c-1), 2^(c-1)):  s = sum_w d_w 2^(c w).  Bucket slot = |d| - 1 in [0, 2^(c-1)).
-__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, int c, int nwin,
-                                                         int rank, int nranks, int32_t* __restrict__ digits,
-                                                         uint32_t* __restrict__ hist) {
+// Recoding without a carry chain: with H = sum_w 2^(c-1) 2^(c w),  d_w = ((s + H) >> c w) mod 2^c  -  2^(c-1)
+// (identical digits to the carry-propagating recode).  C is a template parameter so every shift is a constant and the
+// scalar stays in registers.
+// Canonical scalars are < L < 2^250, so a window that starts at bit c w >= 250 - (c-1) only ever sees digits in
+// [0, 2^(250 - c w)]: a handful of buckets would take all n points (2^20 atomics on 2^9 addresses, thousands of
+// additions per bucket).  Such a window spreads every digit over 2^SUB sub-buckets chosen by the low bits of the point
+// index, so its histogram, scatter and accumulation look like any other window's; msm_fold_kernel sums the sub-buckets
+// back before the reduction.
+__host__ __device__ constexpr int short_window_sub_bits(int c, int w) {
+  const int ba = 250 - c * w < 0 ? 0 : 250 - c * w;
+  return ba < c - 1 ? (c - 1) - ba : 0;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, int rank, int nranks,
+                                                         int32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+  constexpr int NWIN = (256 + C - 1) / C;
+  constexpr uint32_t HALF = 1u << (C - 1), MASK = (1u << C) - 1u, NB = HALF;
   size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  Fe s = fe_load52(scalars + 5 * i);
-  const uint32_t half = 1u << (c - 1);
-  const uint32_t mask = (1u << c) - 1u;
-  const uint32_t nb = half;
-  uint32_t carry = 0;
-  int wl = 0;
-  for (int w = 0; w < nwin; w++) {
-    int bit = w * c;
-    int word = bit >> 5, sh = bit & 31;
-    uint32_t raw = 0;
-    if (word < 8) {
-      uint64_t two = s.w[word];
-      if (word + 1 < 8) two |= (uint64_t)s.w[word + 1] << 32;
-      raw = (uint32_t)(two >> sh) & mask;
+  const uint64_t* sp = scalars + 5 * i;
+  const uint64_t l0 = sp[0], l1 = sp[1], l2 = sp[2], l3 = sp[3], l4 = sp[4];
+  // 5 x 52-bit limbs -> 64-bit words, plus H (compile-time constant), 320 bits
+  uint64_t v[5];
+  v[0] = l0 | (l1 << 52);
+  v[1] = (l1 >> 12) | (l2 << 40);
+  v[2] = (l2 >> 24) | (l3 << 28);
+  v[3] = (l3 >> 36) | (l4 << 16);
+  v[4] = 0;
+  {
+    uint64_t h[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < NWIN; w++) { const int bit = C - 1 + C * w; h[bit >> 6] |= 1ull << (bit & 63); }
+    uint64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      uint64_t t = v[k] + h[k];
+      uint64_t c1 = t < v[k];
+      v[k] = t + carry;
+      carry = c1 | (v[k] < t);
     }
-    raw += carry;
-    int32_t d;
-    if (raw >= half) { d = (int32_t)raw - (int32_t)(1u << c); carry = 1; } else { d = (int32_t)raw; carry = 0; }
+  }
+  int wl = 0;
+#pragma unroll
+  for (int w = 0; w < NWIN; w++) {
     if (w % nranks == rank) {
-      digits[(size_t)wl * n + i] = d;
+      const int bit = C * w, word = bit >> 6, sh = bit & 63;
+      uint64_t x = v[word] >> sh;
+      if (sh + C > 64 && word + 1 < 5) x |= v[word + 1] << (64 - sh);
+      const int32_t d = (int32_t)((uint32_t)x & MASK) - (int32_t)HALF;
+      int32_t key = d;                                        // sign * (bucket slot + 1), 0 = skip
       if (d != 0) {
         uint32_t slot = (uint32_t)(d < 0 ? -d : d) - 1u;
-        atomicAdd(&hist[(size_t)wl * nb + slot], 1u);
+        const int SUB = short_window_sub_bits(C, w);      // top window(s) of a 250-bit scalar: few distinct digits
+        if (SUB > 0) slot = ((slot << SUB) | ((uint32_t)i & ((1u << SUB) - 1u))) & (NB - 1u);
+        key = d < 0 ? -(int32_t)(slot + 1u) : (int32_t)(slot + 1u);
+        atomicAdd(&hist[(size_t)wl * NB + slot], 1u);
       }
+      digits[(size_t)wl * n + i] = key;
       wl++;
     }
   }
 }
 
-// ---- exclusive scan of each window's histogram (one block of 1024 threads per local window) -----------------------
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ offs,
-                                                        uint32_t* __restrict__ cursor, int nb) {
-  __shared__ uint32_t part[1024];
-  const int wl = blockIdx.x;
+// ---- exclusive scan of each window's histogram (one block of SCAN_TPB threads per local window) -----------------------
+// Thread t owns PER = nb / SCAN_TPB consecutive counters (16-byte loads), warps scan by shuffle, one shared-memory hop.
+constexpr int SCAN_TPB = 1024;
+__global__ void __launch_bounds__(SCAN_TPB) msm_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ offs,
+                                                            uint32_t* __restrict__ cursor, int nb) {
+  __shared__ uint32_t wtot[32];
+  const int wl = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const uint32_t* h = hist + (size_t)wl * nb;
-  const int per = (nb + 1023) / 1024;
-  const int lo = threadIdx.x * per;
+  const int per = nb >= 4 * SCAN_TPB ? nb / SCAN_TPB : 4;      // multiple of 4 (nb is a power of two >= 128)
+  const int lo = t * per;
   uint32_t sum = 0;
-  for (int k = 0; k < per; k++) if (lo + k < nb) sum += h[lo + k];
-  part[threadIdx.x] = sum;
+  if (lo < nb) for (int k = 0; k < per; k += 4) { uint4 q = *reinterpret_cast<const uint4*>(h + lo + k); sum += q.x + q.y + q.z + q.w; }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+  if (lane == 31) wtot[wid] = inc;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    uint32_t v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
+  if (wid == 0) {
+    uint32_t x = wtot[lane], y = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, y, d); if (lane >= d) y += o; }
+    wtot[lane] = y - x;                                         // exclusive warp offsets
   }
-  uint32_t run = part[threadIdx.x] - sum;
-  for (int k = 0; k < per; k++) {
-    if (lo + k < nb) {
-      offs[(size_t)wl * nb + lo + k] = run;
-      cursor[(size_t)wl * nb + lo + k] = run;
-      run += h[lo + k];
-    }
+  __syncthreads();
+  uint32_t run = wtot[wid] + inc - sum;
+  if (lo < nb) for (int k = 0; k < per; k += 4) {
+    uint4 q = *reinterpret_cast<const uint4*>(h + lo + k);
+    uint4 o; o.x = run; o.y = run + q.x; o.z = o.y + q.y; o.w = o.z + q.z; run = o.w + q.w;
+    *reinterpret_cast<uint4*>(offs + (size_t)wl * nb + lo + k) = o;
+    *reinterpret_cast<uint4*>(cursor + (size_t)wl * nb + lo + k) = o;
   }
 }
 
@@ -326,82 +361,155 @@ __device__ __forceinline__ Pt shfl_down_pt(const Pt& v, int d) {
   return o;
 }
 
-// ---- bucket reduction  W = sum_k (k+1) B_k,  two warp-cooperative levels ------------------------------------------
-// A warp owns RCH = 32 * RQ consecutive items.  Lane l walks its RQ items with the running-sum trick
-//   c_l = sum_j I_j,   a_l = sum_j j I_j          (2 RQ - 1 additions, serial)
-// then the warp takes a suffix scan S_l = sum_{i >= l} c_i (5 shuffle steps) and one tree sum:
-//   sum_k (k - base) I_k = sum_l (a_l + RQ * l * c_l) = sum_l a_l + RQ * sum_{l >= 1} S_l.
-// Depth per level ~ 2 RQ + 14 additions instead of the 5 chunk + 5 tree launches this replaces.
-constexpr int RQ = 8;
-constexpr int RCH = 32 * RQ;      // 256 buckets per warp at level 0
+// ---- short windows: sum the 2^sub sub-buckets of every digit back into one bucket ---------------------------------
+// one warp per real bucket k < nb >> sub:  out[k] = sum_t buckets[(k << sub) | t]
+__global__ void __launch_bounds__(128) msm_fold_kernel(const uint32_t* __restrict__ buckets, int nb, int sub, uint32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const size_t k = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (k >= (size_t)(nb >> sub)) return;
+  const uint32_t* base = buckets + 32 * (k << sub);
+  Pt acc = pt_identity_mont();
+  bool have = false;
+  for (int t = lane; t < (1 << sub); t += 32) {
+    Pt x = ld_pt(base + 32 * (size_t)t);
+    if (!have) { acc = x; have = true; } else acc = pt_add_ni(acc, x);
+  }
+  acc = warp_sum_pt(acc);
+  if (lane == 0) st_pt(out + 32 * k, acc);
+}
+// buckets[k] = k < nreal ? folded[k] : identity
+__global__ void __launch_bounds__(256) msm_unfold_kernel(const uint32_t* __restrict__ folded, int nb, int nreal, uint32_t* __restrict__ buckets) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= nb) return;
+  Pt p = k < nreal ? ld_pt(folded + 32 * (size_t)k) : pt_identity_mont();
+  st_pt(buckets + 32 * (size_t)k, p);
+}
 
-template <int Q, bool WITH_PLAIN>
-__device__ __forceinline__ void warp_weighted(const uint32_t* __restrict__ items, const uint32_t* __restrict__ plain,
-                                              int n_items, int lane, Pt& total, Pt& weighted, Pt& plain_sum) {
-  // lane's items: indices lane*Q .. lane*Q+Q-1  (identity beyond n_items)
+// ---- bucket reduction  W = sum_k (k+1) B_k  by digit marginals ("cube" reduction) ----------------------------------
+// Write the bucket index as four digits  k = k3 2^(A0+a1+a2) + k2 2^(A0+a1) + k1 2^A0 + k0  (k0: lane, k1: warp in
+// block, k2 / k3: low / high bits of the block index).  Then
+//     sum_k (k+1) B_k = 2^(A0+a1+a2) sum_v v M3[v] + 2^(A0+a1) sum_v v M2[v] + 2^A0 sum_v v M1[v] + sum_v (v+1) M0[v]
+// where Md[v] is the plain sum of all buckets whose digit d equals v.  Plain sums are trees (depth 5 + a1 in stage 1,
+// <= 8 in stage 2a), every weighted sum has at most 32 terms (stage 2b, depth ~13) and the powers of two are applied
+// for free by the window chain: ~29 dependent point additions instead of ~110 for a chunked running sum.
+constexpr int A0 = 5;
+
+// warp-cooperative weighted sum over n_items <= 32 Q items: lane l owns items l*Q .. l*Q+Q-1.
+//   total = sum_j I_j (lane 0),  weighted = sum_j j I_j (lane 0)
+template <int Q>
+__device__ __forceinline__ void warp_weighted(const uint32_t* __restrict__ items, int n_items, int lane, Pt& total, Pt& weighted) {
   const int lo = lane * Q;
-  Pt run = pt_identity_mont(), acc = pt_identity_mont(), pl = pt_identity_mont();
+  Pt run = pt_identity_mont(), acc = pt_identity_mont();
 #pragma unroll 1
   for (int j = Q - 1; j >= 0; j--) {
     const int k = lo + j;
-    if (k < n_items) {
-      run = pt_add_ni(run, ld_pt(items + 32 * (size_t)k));
-      if (WITH_PLAIN) pl = pt_add_ni(pl, ld_pt(plain + 32 * (size_t)k));
-    }
+    if (k < n_items) run = pt_add_ni(run, ld_pt(items + 32 * (size_t)k));
     if (j > 0) acc = pt_add_ni(acc, run);
   }
-  // suffix scan of run over lanes
-  Pt S = run;
+  Pt S = run;                                  // suffix scan of the lane totals
 #pragma unroll 1
   for (int d = 1; d < 32; d <<= 1) {
     Pt o = shfl_down_pt(S, d);
     Pt t = pt_add_ni(S, o);
     if (lane + d < 32) S = t;
   }
-  // z = Q * (lane >= 1 ? S : 0) + acc
-  Pt z = (lane >= 1) ? S : pt_identity_mont();
-#pragma unroll
-  for (int q = Q; q > 1; q >>= 1) z = pt_double_ni(z);
-  z = pt_add_ni(z, acc);
-  weighted = warp_sum_pt(z);
-  total = S;                 // valid on lane 0
-  if (WITH_PLAIN) plain_sum = warp_sum_pt(pl);
-}
-
-// level 0: one warp per chunk of RCH buckets -> chunk sum C_t and chunk-local weighted sum Wt_t = sum (k - base) B_k
-__global__ void __launch_bounds__(128) msm_reduce0_kernel(const uint32_t* __restrict__ buckets, int nb, int nchunk, int nwl,
-                                                          uint32_t* __restrict__ csum, uint32_t* __restrict__ wloc) {
-  const int lane = threadIdx.x & 31;
-  const size_t g = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (g >= (size_t)nwl * nchunk) return;
-  const size_t wl = g / nchunk;
-  const int t = (int)(g - wl * nchunk);
-  const int base = t * RCH;
-  Pt total, weighted, unused;
-  warp_weighted<RQ, false>(buckets + 32 * (wl * nb + base), nullptr, min(RCH, nb - base), lane, total, weighted, unused);
-  if (lane == 0) { st_pt(csum + 32 * g, total); st_pt(wloc + 32 * g, weighted); }
-}
-
-// level 1: one warp per window.  W = sum_t [ Wt_t + (t RCH + 1) C_t ] = sum_t Wt_t + sum_t C_t + RCH * sum_t t C_t
-template <int Q1>
-__device__ __forceinline__ Pt reduce1_body(const uint32_t* __restrict__ csum, const uint32_t* __restrict__ wloc, int nchunk, int lane) {
-  Pt total, weighted, plain;
-  warp_weighted<Q1, true>(csum, wloc, nchunk, lane, total, weighted, plain);
+  Pt z = (lane >= 1) ? S : pt_identity_mont(); // sum_l l c_l = sum_{l >= 1} S_l
 #pragma unroll 1
-  for (int q = RCH; q > 1; q >>= 1) weighted = pt_double_ni(weighted);
-  return pt_add_ni(pt_add_ni(weighted, total), plain);   // valid on lane 0
+  for (int q = Q; q > 1; q >>= 1) z = pt_double_ni(z);
+  if (Q > 1) z = pt_add_ni(z, acc);
+  weighted = warp_sum_pt(z);
+  total = S;
 }
-__global__ void __launch_bounds__(32) msm_reduce1_kernel(const uint32_t* __restrict__ csum, const uint32_t* __restrict__ wloc,
-                                                         int nchunk, uint32_t* __restrict__ wsum) {
-  const int lane = threadIdx.x;
+
+// stage 1: one block per (window, k2): 2^a1 warps x 32 lanes, one bucket per thread.
+//   pm1[blk][warp] = sum over lanes,  pm0[blk][lane] = sum over warps,  tot[blk] = sum of the block's buckets
+__global__ void __launch_bounds__(256) msm_cube1_kernel(const uint32_t* __restrict__ buckets, int a1, uint32_t* __restrict__ tot,
+                                                        uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0) {
+  extern __shared__ uint4 cube_sm[];           // [8 uint4 of a point][warp][lane]  +  [8][warp] row sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = 1 << a1;
+  const size_t blk = blockIdx.x;
+  uint4* colbuf = cube_sm;
+  uint4* rowbuf = cube_sm + 8 * nw * 32;
+  Pt v = ld_pt(buckets + 32 * (blk * (size_t)(nw * 32) + threadIdx.x));
+  auto put = [&](uint4* base, int stride, int idx, const Pt& p) {
+    base[0 * stride + idx] = make_uint4(p.X.w[0], p.X.w[1], p.X.w[2], p.X.w[3]); base[1 * stride + idx] = make_uint4(p.X.w[4], p.X.w[5], p.X.w[6], p.X.w[7]);
+    base[2 * stride + idx] = make_uint4(p.Y.w[0], p.Y.w[1], p.Y.w[2], p.Y.w[3]); base[3 * stride + idx] = make_uint4(p.Y.w[4], p.Y.w[5], p.Y.w[6], p.Y.w[7]);
+    base[4 * stride + idx] = make_uint4(p.Z.w[0], p.Z.w[1], p.Z.w[2], p.Z.w[3]); base[5 * stride + idx] = make_uint4(p.Z.w[4], p.Z.w[5], p.Z.w[6], p.Z.w[7]);
+    base[6 * stride + idx] = make_uint4(p.T.w[0], p.T.w[1], p.T.w[2], p.T.w[3]); base[7 * stride + idx] = make_uint4(p.T.w[4], p.T.w[5], p.T.w[6], p.T.w[7]);
+  };
+  auto get = [&](const uint4* base, int stride, int idx) {
+    Pt p; uint4 q;
+    q = base[0 * stride + idx]; p.X.w[0] = q.x; p.X.w[1] = q.y; p.X.w[2] = q.z; p.X.w[3] = q.w;
+    q = base[1 * stride + idx]; p.X.w[4] = q.x; p.X.w[5] = q.y; p.X.w[6] = q.z; p.X.w[7] = q.w;
+    q = base[2 * stride + idx]; p.Y.w[0] = q.x; p.Y.w[1] = q.y; p.Y.w[2] = q.z; p.Y.w[3] = q.w;
+    q = base[3 * stride + idx]; p.Y.w[4] = q.x; p.Y.w[5] = q.y; p.Y.w[6] = q.z; p.Y.w[7] = q.w;
+    q = base[4 * stride + idx]; p.Z.w[0] = q.x; p.Z.w[1] = q.y; p.Z.w[2] = q.z; p.Z.w[3] = q.w;
+    q = base[5 * stride + idx]; p.Z.w[4] = q.x; p.Z.w[5] = q.y; p.Z.w[6] = q.z; p.Z.w[7] = q.w;
+    q = base[6 * stride + idx]; p.T.w[0] = q.x; p.T.w[1] = q.y; p.T.w[2] = q.z; p.T.w[3] = q.w;
+    q = base[7 * stride + idx]; p.T.w[4] = q.x; p.T.w[5] = q.y; p.T.w[6] = q.z; p.T.w[7] = q.w;
+    return p;
+  };
+  put(colbuf, nw * 32, warp * 32 + lane, v);
+  Pt r = warp_sum_pt(v);                       // row sum (lane 0)
+  if (lane == 0) { st_pt(pm1 + 32 * (blk * nw + warp), r); put(rowbuf, nw, warp, r); }
+  __syncthreads();
+  // column sums over the warps (warp 0 ends up with them) and, on the last warp, the block total from the row sums
+  Pt t = pt_identity_mont();
+  if (warp == nw - 1 && lane < nw) t = get(rowbuf, nw, lane);
+  for (int s2 = nw >> 1; s2 >= 1; s2 >>= 1) {
+    if (warp < s2) {
+      v = pt_add_ni(v, get(colbuf, nw * 32, (warp + s2) * 32 + lane));
+      if (s2 > 1) put(colbuf, nw * 32, warp * 32 + lane, v);
+    } else if (warp == nw - 1) {
+      Pt o = shfl_down_pt(t, s2);
+      t = pt_add_ni(t, o);
+    }
+    __syncthreads();
+  }
+  if (nw == 1) t = r;                          // single warp: total = its row sum
+  if (warp == 0) st_pt(pm0 + 32 * (blk * 32 + lane), v);
+  if (warp == nw - 1 && lane == 0) st_pt(tot + 32 * blk, t);
+}
+
+// stage 2a: one warp per marginal sum.  Tasks of a window: M1[2^a1] and M0[32] over the window's nblk blocks, then
+// M2[2^a2] and M3[2^a3] over the block totals (block index = k3 2^a2 + k2).  marg layout: [M1 | M0 | M2 | M3].
+__global__ void __launch_bounds__(128) msm_cube2a_kernel(const uint32_t* __restrict__ tot, const uint32_t* __restrict__ pm1,
+                                                         const uint32_t* __restrict__ pm0, int a1, int a2, int a3, int nwl,
+                                                         uint32_t* __restrict__ marg) {
+  const int lane = threadIdx.x & 31;
+  const int nw = 1 << a1, n2 = 1 << a2, n3 = 1 << a3, nblk = n2 * n3, ntask = nw + 32 + n2 + n3;
+  const size_t g = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (g >= (size_t)nwl * ntask) return;
+  const size_t wl = g / ntask;
+  const int task = (int)(g - wl * ntask);
+  const uint32_t* base; size_t stride; int count;
+  if (task < nw)                { base = pm1 + 32 * ((wl * nblk) * nw + task);        stride = nw; count = nblk; }
+  else if (task < nw + 32)      { base = pm0 + 32 * ((wl * nblk) * 32 + (task - nw)); stride = 32; count = nblk; }
+  else if (task < nw + 32 + n2) { base = tot + 32 * (wl * nblk + (task - nw - 32));   stride = n2; count = n3; }
+  else                          { base = tot + 32 * (wl * nblk + (size_t)(task - nw - 32 - n2) * n2); stride = 1; count = n2; }
+  Pt acc = pt_identity_mont();
+  bool have = false;
+  for (int b = lane; b < count; b += 32) {
+    Pt x = ld_pt(base + 32 * ((size_t)b * stride));
+    if (!have) { acc = x; have = true; } else acc = pt_add_ni(acc, x);
+  }
+  acc = warp_sum_pt(acc);
+  if (lane == 0) st_pt(marg + 32 * (wl * ntask + task), acc);
+}
+
+// stage 2b: four warps per window: comp[0] = sum v M3[v], comp[1] = sum v M2[v], comp[2] = sum v M1[v],
+// comp[3] = sum (v+1) M0[v]
+__global__ void __launch_bounds__(128) msm_cube2b_kernel(const uint32_t* __restrict__ marg, int a1, int a2, int a3, uint32_t* __restrict__ comp) {
+  const int lane = threadIdx.x & 31, which = threadIdx.x >> 5;
+  const int nw = 1 << a1, n2 = 1 << a2, n3 = 1 << a3, ntask = nw + 32 + n2 + n3;
   const size_t wl = blockIdx.x;
-  const uint32_t* c = csum + 32 * (wl * nchunk);
-  const uint32_t* w = wloc + 32 * (wl * nchunk);
-  Pt r;
-  if (nchunk <= 32) r = reduce1_body<1>(c, w, nchunk, lane);
-  else if (nchunk <= 64) r = reduce1_body<2>(c, w, nchunk, lane);
-  else r = reduce1_body<4>(c, w, nchunk, lane);
-  if (lane == 0) st_pt(wsum + 32 * wl, r);
+  const uint32_t* m = marg + 32 * (wl * ntask);
+  Pt total, weighted;
+  if (which == 0)      warp_weighted<1>(m + 32 * (nw + 32 + n2), n3, lane, total, weighted);
+  else if (which == 1) warp_weighted<1>(m + 32 * (nw + 32), n2, lane, total, weighted);
+  else if (which == 2) warp_weighted<1>(m, nw, lane, total, weighted);
+  else { warp_weighted<1>(m + 32 * nw, 32, lane, total, weighted); weighted = pt_add_ni(weighted, total); }
+  if (lane == 0) st_pt(comp + 32 * (wl * 4 + which), weighted);
 }
 
 // ---- window chain: acc = 2^(c w) - weighted sum of this rank's window sums, four lanes per point operation ----------
@@ -419,23 +527,66 @@ __device__ __forceinline__ Fe quad_stage2(const Fe& E, const Fe& F, const Fe& G,
   }
   return mont_mul<M>(u, v);
 }
-__device__ __forceinline__ Fe quad_double(const Fe& c, int q, int qbase) {
+// lazy linear combinations for the chain: no conditional subtraction, results < 4m (inputs canonical);
+// mont_mul accepts them because the product of any two stays below R m = 2^256 m (16 m^2 > 8 m^2).
+__device__ __forceinline__ Fe fe_dbl_lazy(const Fe& a) {                 // 2a < 2m
+  Fe r;
+#pragma unroll
+  for (int k = 7; k > 0; k--) r.w[k] = __funnelshift_l(a.w[k - 1], a.w[k], 1);
+  r.w[0] = a.w[0] << 1;
+  return r;
+}
+// a - b + K m  (K = 1 or 2), a < K' m, b < K m
+template <int K>
+__device__ __forceinline__ Fe fe_sub_lazy(const Fe& a, const Fe& b) {
   typedef ModP M;
-  Fe x = shfl_fe(c, qbase), y = shfl_fe(c, qbase + 1);
-  Fe in = c;
-  if (q == 3) in = fe_add<M>(x, y);
-  Fe s = mont_mul<M>(in, in);                                  // A, B, ZZ, (X+Y)^2 on lanes 0..3
-  Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), ZZ = shfl_fe(s, qbase + 2), SS = shfl_fe(s, qbase + 3);
-  Fe C = fe_add<M>(ZZ, ZZ);
-  Fe D = fe_neg<M>(A);
-  Fe E = fe_sub<M>(fe_sub<M>(SS, A), B);
-  Fe G = fe_add<M>(D, B);
-  Fe F = fe_sub<M>(G, C);
-  Fe H = fe_sub<M>(D, B);
+  constexpr uint64_t m01 = ((uint64_t)M::M1 << 32 | M::M0), m23 = ((uint64_t)M::M3 << 32 | M::M2);
+  // K * m as words (K <= 2: no overflow of the 4 low words into word 4 beyond a carry)
+  constexpr unsigned __int128 lowK = ((unsigned __int128)m23 << 64 | m01) * K;
+  constexpr uint32_t k0 = (uint32_t)lowK, k1 = (uint32_t)(lowK >> 32), k2 = (uint32_t)(lowK >> 64), k3 = (uint32_t)(lowK >> 96),
+                     k4 = (uint32_t)(lowK >> 128), k7 = M::M7 * K;
+  Fe r;
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, 0;\n\t"
+      "addc.cc.u32 %6, %14, 0;\n\t"
+      "addc.u32    %7, %15, %21;\n\t"
+      "sub.cc.u32  %0, %0, %22;\n\t"
+      "subc.cc.u32 %1, %1, %23;\n\t"
+      "subc.cc.u32 %2, %2, %24;\n\t"
+      "subc.cc.u32 %3, %3, %25;\n\t"
+      "subc.cc.u32 %4, %4, %26;\n\t"
+      "subc.cc.u32 %5, %5, %27;\n\t"
+      "subc.cc.u32 %6, %6, %28;\n\t"
+      "subc.u32    %7, %7, %29;\n\t"
+      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
+      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
+        "r"(k0), "r"(k1), "r"(k2), "r"(k3), "r"(k4), "r"(k7),
+        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
+  return r;
+}
+__device__ __noinline__ Fe quad_double(Fe c, int q, int qbase) {
+  typedef ModP M;
+  // stage 1: X^2, Y^2, Z^2 on lanes 0..2 and T Z (= X Y, so E = 2 T Z) on lane 3
+  Fe z = shfl_fe(c, qbase + 2);
+  Fe in2 = c;
+  if (q == 3) in2 = z;
+  Fe s = mont_mul<M>(c, in2);
+  Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), ZZ = shfl_fe(s, qbase + 2), TZ = shfl_fe(s, qbase + 3);
+  Fe E = fe_dbl_lazy(TZ);                      // < 2m
+  Fe C = fe_dbl_lazy(ZZ);                      // < 2m
+  Fe G = fe_sub_lazy<1>(B, A);                 // B - A + m      in (0, 2m)
+  Fe F = fe_sub_lazy<2>(G, C);                 // G - C + 2m     in (0, 4m)
+  Fe ApB = fe_add<M>(A, B);                    // canonical
+  Fe zero{{0, 0, 0, 0, 0, 0, 0, 0}};
+  Fe H = fe_sub_lazy<1>(zero, ApB);            // m - (A + B)    in (0, m]
   return quad_stage2(E, F, G, H, q);
 }
 // c (distributed over the quad) += the full point p (every lane holds all of p)
-__device__ __forceinline__ Fe quad_add(const Fe& c, const Pt& p, int q, int qbase) {
+__device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
   typedef ModP M;
   Fe x1 = shfl_fe(c, qbase), y1 = shfl_fe(c, qbase + 1);
   Fe u, v;
@@ -452,11 +603,15 @@ __device__ __forceinline__ Fe quad_add(const Fe& c, const Pt& p, int q, int qbas
   return quad_stage2(E, F, G, H, q);
 }
 
-// One warp.  acc (in/out, extended Montgomery words) is the running sum already scaled to this group's top window.
-//   for i in 0..ng-1:  if (i > 0) acc = 2^gap_in acc;   acc += wsum[i]       (group windows in descending order)
-//   acc = 2^gap_post acc
+// One warp.  acc (in/out, extended Montgomery words) is the running sum, already scaled to 2^(A0+a1+a2) times the unit
+// of this group's top window.  Each window contributes four components (msm_cube2b):
+//   comp0 2^(A0+a1+a2) + comp1 2^(A0+a1) + comp2 2^A0 + comp3.
+//   for i in 0..ng-1 (group windows in descending order):
+//     if (i > 0) acc = 2^(gap_in - A0 - a1 - a2) acc
+//     acc += comp0;  acc = 2^a2 acc;  acc += comp1;  acc = 2^a1 acc;  acc += comp2;  acc = 2^A0 acc;  acc += comp3
+//   acc = 2^gap_post acc          (gap_post already excludes A0 + a1 + a2 when another group follows)
 // first != 0: acc starts as the identity.  out52 != nullptr: also store the result in the ABI layout.
-__global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ wsum, int ng, int wsum_step, int first,
+__global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ comp, int ng, int first, int a1, int a2,
                                                        int gap_in, int gap_post, uint32_t* __restrict__ acc_io,
                                                        uint64_t* __restrict__ out52) {
   const int lane = threadIdx.x;
@@ -465,12 +620,14 @@ __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restric
   Fe c = (q == 0) ? a0.X : (q == 1 ? a0.Y : (q == 2 ? a0.Z : a0.T));
 #pragma unroll 1
   for (int i = 0; i < ng; i++) {
-    if (i > 0) {
+    const uint32_t* cw = comp - 128 * (ptrdiff_t)i;          // windows in descending order
 #pragma unroll 1
-      for (int j = 0; j < gap_in; j++) c = quad_double(c, q, qbase);
+    for (int part = 0; part < 4; part++) {
+      int nd = part == 0 ? (i > 0 ? gap_in - A0 - a1 - a2 : 0) : (part == 1 ? a2 : (part == 2 ? a1 : A0));
+#pragma unroll 1
+      for (int j = 0; j < nd; j++) c = quad_double(c, q, qbase);
+      c = quad_add(c, ld_pt(cw + 32 * part), q, qbase);
     }
-    Pt w = ld_pt(wsum + 32 * ((ptrdiff_t)i * wsum_step));
-    c = quad_add(c, w, q, qbase);
   }
 #pragma unroll 1
   for (int j = 0; j < gap_post; j++) c = quad_double(c, q, qbase);
@@ -523,11 +680,20 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o_offs = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_cursor = o; o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_buckets = o; o = align_up(o + (size_t)nwl * nb * 128, 256);
-    const int nchunk = (nb + RCH - 1) / RCH;
-    size_t o_csum = o; o = align_up(o + (size_t)nwl * nchunk * 128, 256);
-    size_t o_wloc = o; o = align_up(o + (size_t)nwl * nchunk * 128, 256);
+    const int bits = c - 1;                                     // nb = 2^bits, bits in 7..15
+    const int a1 = bits - A0 < 3 ? bits - A0 : 3;               // warps per cube block = 2^a1
+    const int ab = bits - A0 - a1;                              // block-index bits, split into k2 (a2) and k3 (a3)
+    const int a2 = ab < 4 ? ab : 4, a3 = ab - a2;
+    const int nblk = 1 << ab;                                   // cube blocks per window
+    const int nw1 = 1 << a1;
+    const int ntask = nw1 + 32 + (1 << a2) + (1 << a3);
+    size_t o_tot = o;  o = align_up(o + (size_t)nwl * nblk * 128, 256);
+    size_t o_pm1 = o;  o = align_up(o + (size_t)nwl * nblk * nw1 * 128, 256);
+    size_t o_pm0 = o;  o = align_up(o + (size_t)nwl * nblk * 32 * 128, 256);
+    size_t o_marg = o; o = align_up(o + (size_t)nwl * ntask * 128, 256);
+    size_t o_fold = o; o = align_up(o + (size_t)nb * 128, 256);
     size_t o_acc = o;  o = align_up(o + 128, 256);
-    size_t o_wsum = o; o = align_up(o + (size_t)nwl * 128, 256);
+    size_t o_comp = o; o = align_up(o + (size_t)nwl * 4 * 128, 256);
     if (o > ctx->msm_ws_bytes) {
       if (ctx->msm_ws) ZC_CUDA(ctx, cudaFree(ctx->msm_ws));
       ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0;
@@ -546,56 +712,126 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     uint32_t *offs = (uint32_t*)(ws + o_offs);
     uint32_t *cursor = (uint32_t*)(ws + o_cursor);
     uint32_t *buckets = (uint32_t*)(ws + o_buckets);
-    uint32_t *csum = (uint32_t*)(ws + o_csum);
-    uint32_t *wloc = (uint32_t*)(ws + o_wloc);
+    uint32_t *btot = (uint32_t*)(ws + o_tot);
+    uint32_t *pm1 = (uint32_t*)(ws + o_pm1);
+    uint32_t *pm0 = (uint32_t*)(ws + o_pm0);
+    uint32_t *marg = (uint32_t*)(ws + o_marg);
+    uint32_t *folded = (uint32_t*)(ws + o_fold);
     uint32_t *acc = (uint32_t*)(ws + o_acc);
-    uint32_t *wsum = (uint32_t*)(ws + o_wsum);
+    uint32_t *comp = (uint32_t*)(ws + o_comp);
     cudaStream_t st = ctx->stream;
     if (!ctx->side_stream) {
       ZC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-      for (int i = 0; i < MAX_GROUPS + 1; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+      ZC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->chain_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 16; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     }
-    cudaStream_t side = ctx->side_stream;
+    // st: digits, sort, accumulation.  side: operand preparation, then stitch + reduce of each group.  chain: the
+    // serial window chain.  Events: ev[0] fork, ev[1] prep done, ev[2+g] group g accumulated, ev[6+g] group g reduced,
+    // ev[10] chain done.
+    cudaStream_t side = ctx->side_stream, chain = ctx->chain_stream;
 
-    ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwl * nb * 4, st));
-    ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
-    msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(points, cached, n); ctx->launches++;
-    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars, n, c, nwin, rank, nranks, digits, hist); ctx->launches++;
-    msm_scan_kernel<<<nwl, 1024, 0, st>>>(hist, offs, cursor, nb); ctx->launches++;
-    {
-      size_t tot = n * (size_t)nwl;
-      msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); ctx->launches++;
+    // The ~25 launches and the two-stream fork/join of one MSM are recorded once into a CUDA graph and replayed while
+    // the call's arguments stay the same (repeated proofs over resident generators): one launch instead of a launch-
+    // latency-bound sequence -- at 8 ranks the per-rank kernels are short enough for launch gaps to rival the math.
+    uint64_t nlaunch = 0;
+    auto enqueue = [&]() -> int32_t {
+      ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwl * nb * 4, st));
+      ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
+      ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+      ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[0], 0));
+      msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++;
+      ZC_CUDA(ctx, cudaEventRecord(ctx->ev[1], side));
+      {
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        switch (c) {
+  #define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, rank, nranks, digits, hist); break;
+          ZC_DIGITS_CASE(8) ZC_DIGITS_CASE(9) ZC_DIGITS_CASE(10) ZC_DIGITS_CASE(11) ZC_DIGITS_CASE(12)
+          ZC_DIGITS_CASE(13) ZC_DIGITS_CASE(14) ZC_DIGITS_CASE(15) ZC_DIGITS_CASE(16)
+  #undef ZC_DIGITS_CASE
+        }
+        nlaunch++;
+      }
+      msm_scan_kernel<<<nwl, SCAN_TPB, 0, st>>>(hist, offs, cursor, nb); nlaunch++;
+      {
+        size_t tot = n * (size_t)nwl;
+        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); nlaunch++;
+      }
+      // Window groups, top-down.  Local window wl is global window rank + nranks * wl.  After a group's buckets are
+      // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
+      // next group's top window (or, after the last group, by 2^(c * rank)) while the main stream accumulates the next group.
+      const int ngroups = nwl < MAX_GROUPS ? nwl : MAX_GROUPS;
+      int hi = nwl;
+      for (int g = 0; g < ngroups; g++) {
+        const int gsz = (hi + (ngroups - g) - 1) / (ngroups - g);
+        const int lo = hi - gsz;
+        const size_t tot = (size_t)gsz * nb;
+        const size_t tseg = (size_t)gsz * nseg;
+        const uint32_t *g_sorted = sorted + (size_t)lo * n_pad, *g_offs = offs + (size_t)lo * nb, *g_hist = hist + (size_t)lo * nb;
+        uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg), *g_partT = partT + 32 * ((size_t)lo * nseg);
+        uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
+        if (g == 0) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
+        msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, gsz, nb, g_buckets, g_partH, g_partT); nlaunch++;
+        // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
+        // stream, under the next group's accumulation
+        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
+        ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
+        msm_fix_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, side>>>(g_offs, g_hist, nseg, gsz, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++;
+        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++;
+        for (int wl = lo; wl < hi; wl++) {                        // short (top) windows: sum sub-buckets back
+          const int sub = short_window_sub_bits(c, rank + nranks * wl);
+          if (sub > 0) {
+            uint32_t *wb = buckets + 32 * ((size_t)wl * nb);
+            msm_fold_kernel<<<(unsigned)(((nb >> sub) + 3) / 4), 128, 0, side>>>(wb, nb, sub, folded); nlaunch++;
+            msm_unfold_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, side>>>(folded, nb, nb >> sub, wb); nlaunch++;
+          }
+        }
+        const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
+        msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, side>>>(g_buckets, a1, btot + 32 * ((size_t)lo * nblk),
+            pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++;
+        msm_cube2a_kernel<<<(unsigned)(((size_t)gsz * ntask + 3) / 4), 128, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
+            pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz,
+            marg + 32 * ((size_t)lo * ntask)); nlaunch++;
+        msm_cube2b_kernel<<<gsz, 128, 0, side>>>(marg + 32 * ((size_t)lo * ntask), a1, a2, a3, comp + 128 * (size_t)lo); nlaunch++;
+        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[6 + g], side));
+        ZC_CUDA(ctx, cudaStreamWaitEvent(chain, ctx->ev[6 + g], 0));
+        const bool last = (g == ngroups - 1);
+        msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, c * nranks,
+                                             last ? c * rank : c * nranks - A0 - a1 - a2, acc, last ? partial : nullptr); nlaunch++;
+        hi = lo;
+      }
+      ZC_CUDA(ctx, cudaEventRecord(ctx->ev[10], chain));
+      ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[10], 0));
+      ZC_CUDA(ctx, cudaGetLastError());
+      return ZC_OK;
+    };
+    const zc_msm_key key = {points, scalars, n, c, rank, nranks, 0, partial, ctx->msm_ws};
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    ZC_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone) {
+      int32_t rc = enqueue();                                   // the caller is capturing: become part of their graph
+      if (rc) return rc;
+      ctx->launches += nlaunch;
+    } else if (ctx->msm_graph_exec && memcmp(&key, &ctx->msm_key, sizeof(key)) == 0) {
+      ZC_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)ctx->msm_graph_exec, st));
+      ctx->launches += ctx->msm_graph_launches;
+    } else {
+      if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
+      ZC_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int32_t rc = enqueue();
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      ZC_CUDA(ctx, e);
+      cudaGraphExec_t exec = nullptr;
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      ZC_CUDA(ctx, e);
+      ctx->msm_graph_exec = exec;
+      ctx->msm_key = key;
+      ctx->msm_graph_launches = nlaunch;
+      ZC_CUDA(ctx, cudaGraphLaunch(exec, st));
+      ctx->launches += nlaunch;
     }
-    // Window groups, top-down.  Local window wl is global window rank + nranks * wl.  After a group's buckets are
-    // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
-    // next group's top window (or, after the last group, by 2^(c * rank)) while the main stream accumulates the next group.
-    const int ngroups = nwl < MAX_GROUPS ? nwl : MAX_GROUPS;
-    int hi = nwl;
-    for (int g = 0; g < ngroups; g++) {
-      const int gsz = (hi + (ngroups - g) - 1) / (ngroups - g);
-      const int lo = hi - gsz;
-      const size_t tot = (size_t)gsz * nb;
-      const size_t tseg = (size_t)gsz * nseg;
-      const uint32_t *g_sorted = sorted + (size_t)lo * n_pad, *g_offs = offs + (size_t)lo * nb, *g_hist = hist + (size_t)lo * nb;
-      uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg), *g_partT = partT + 32 * ((size_t)lo * nseg);
-      uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
-      msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, gsz, nb, g_buckets, g_partH, g_partT); ctx->launches++;
-      // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
-      // stream, under the next group's accumulation
-      ZC_CUDA(ctx, cudaEventRecord(ctx->ev[g], st));
-      ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[g], 0));
-      msm_fix_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, side>>>(g_offs, g_hist, nseg, gsz, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); ctx->launches++;
-      msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); ctx->launches++;
-      msm_reduce0_kernel<<<(unsigned)(((size_t)gsz * nchunk + 3) / 4), 128, 0, side>>>(g_buckets, nb, nchunk, gsz, csum + 32 * ((size_t)lo * nchunk), wloc + 32 * ((size_t)lo * nchunk)); ctx->launches++;
-      msm_reduce1_kernel<<<gsz, 32, 0, side>>>(csum + 32 * ((size_t)lo * nchunk), wloc + 32 * ((size_t)lo * nchunk), nchunk, wsum + 32 * (size_t)lo); ctx->launches++;
-      const bool last = (g == ngroups - 1);
-      msm_chain_kernel<<<1, 32, 0, side>>>(wsum + 32 * (size_t)(hi - 1), gsz, -1, g == 0 ? 1 : 0, c * nranks, last ? c * rank : c * nranks,
-                                           acc, last ? partial : nullptr); ctx->launches++;
-      hi = lo;
-    }
-    ZC_CUDA(ctx, cudaEventRecord(ctx->ev[MAX_GROUPS], side));
-    ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[MAX_GROUPS], 0));
-    ZC_CUDA(ctx, cudaGetLastError());
   }
 
   if (exchange) {
