@@ -17,6 +17,9 @@
 //   reduce   sum_k (k+1) * B_k per window: multi-level chunked running sums (chunk m), tree sums per level
 //   combine  Horner over the levels and over this rank's windows with 2^c scalings -> one partial point
 //   exchange (sharded only) ncclAllGather of the partial points + fixed-order fold with the reference Add
+#include <stdlib.h>
+#include <vector>
+
 #include "zc_internal.h"
 #include "zc_point.cuh"
 
@@ -266,33 +269,25 @@ __global__ void __launch_bounds__(ACC_TPB) msm_accum_kernel(const uint32_t* __re
   }
 }
 
-// ---- stitch buckets that span several segments; write the identity into empty buckets -----------------------------
+// ---- buckets that span several segments ---------------------------------------------------------------------------
 // bucket range [o, e): s_first = o / SEG, s_last = (e-1) / SEG.  If s_first == s_last the run was complete and is already
 // in buckets[].  Otherwise  sum = (o == s_first*SEG ? H[s_first] : T[s_first]) + H[s_first+1] + ... + H[s_last].
-// Buckets with more than FIX_INLINE partials are queued for msm_heavy_kernel (one warp per bucket, tree sum).
+// Buckets with at most FIX_INLINE partials are stitched on the fly by whoever reads them (load_bucket, used by the
+// first reduction stage); heavier ones are queued here for msm_heavy_kernel (one warp per bucket, tree sum), which
+// writes them into buckets[].
 constexpr int FIX_INLINE = 6;
-__global__ void __launch_bounds__(128) msm_fix_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                      int nseg, int nwl, int nb, const uint32_t* __restrict__ partH,
-                                                      const uint32_t* __restrict__ partT, uint32_t* __restrict__ buckets,
-                                                      uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
-  size_t g = (size_t)blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(256) msm_fixq_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
+                                                       int nwl, int nb, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+  size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= (size_t)nwl * nb) return;
-  const size_t wl = g / nb;
   const uint32_t cnt = hist[g];
-  if (cnt == 0) { st_pt(buckets + 32 * g, pt_identity_mont()); return; }
+  if (cnt == 0) return;
   const uint32_t o = offs[g], e = o + cnt;
   const uint32_t s_first = o / SEG, s_last = (e - 1) / SEG;
-  if (s_first == s_last) return;
   if (s_last - s_first + 1 > FIX_INLINE) {
     uint32_t slot = atomicAdd(heavy_count, 1u);
     heavy_list[slot] = (uint32_t)g;
-    return;
   }
-  const uint32_t* H = partH + 32 * (wl * nseg);
-  const uint32_t* T = partT + 32 * (wl * nseg);
-  Pt acc = ld_pt((o == s_first * SEG ? H : T) + 32 * (size_t)s_first);
-  for (uint32_t s = s_first + 1; s <= s_last; s++) acc = pt_add_fast(acc, ld_pt(H + 32 * (size_t)s));
-  st_pt(buckets + 32 * g, acc);
 }
 
 // Out-of-line point operations for the latency-bound tail kernels (reduce / heavy): one copy of the ~30 KB addition
@@ -300,6 +295,25 @@ __global__ void __launch_bounds__(128) msm_fix_kernel(const uint32_t* __restrict
 // straight-line code and ran at ~8 cycles per instruction).
 __device__ __noinline__ Pt pt_add_ni(Pt p, Pt q) { return pt_add_fast(p, q); }
 __device__ __noinline__ Pt pt_double_ni(Pt p) { return pt_double_fast(p); }
+
+struct BucketSrc {                  // where a group's buckets live (all pointers relative to the group's first window)
+  const uint32_t *offs, *hist, *partH, *partT, *buckets;
+  int nseg, nb;
+};
+// bucket g of the group, stitched from its segment partials when it spans a few segments
+__device__ __forceinline__ Pt load_bucket(const BucketSrc& b, size_t g) {
+  const uint32_t cnt = b.hist[g];
+  if (cnt == 0) return pt_identity_mont();
+  const uint32_t o = b.offs[g], e = o + cnt;
+  const uint32_t s_first = o / SEG, s_last = (e - 1) / SEG;
+  if (s_first == s_last || s_last - s_first + 1 > FIX_INLINE) return ld_pt(b.buckets + 32 * g);
+  const size_t wl = g / b.nb;
+  const uint32_t* H = b.partH + 32 * (wl * b.nseg);
+  const uint32_t* T = b.partT + 32 * (wl * b.nseg);
+  Pt acc = ld_pt((o == s_first * SEG ? H : T) + 32 * (size_t)s_first);
+  for (uint32_t s2 = s_first + 1; s2 <= s_last; s2++) acc = pt_add_ni(acc, ld_pt(H + 32 * (size_t)s2));
+  return acc;
+}
 
 // warp-wide point sum: lane values -> lane 0 (shuffle tree, 5 additions deep)
 __device__ __forceinline__ Pt warp_sum_pt(Pt v) {
@@ -363,15 +377,15 @@ __device__ __forceinline__ Pt shfl_down_pt(const Pt& v, int d) {
 
 // ---- short windows: sum the 2^sub sub-buckets of every digit back into one bucket ---------------------------------
 // one warp per real bucket k < nb >> sub:  out[k] = sum_t buckets[(k << sub) | t]
-__global__ void __launch_bounds__(128) msm_fold_kernel(const uint32_t* __restrict__ buckets, int nb, int sub, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(128) msm_fold_kernel(BucketSrc src, size_t wl, int sub, uint32_t* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const size_t k = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (k >= (size_t)(nb >> sub)) return;
-  const uint32_t* base = buckets + 32 * (k << sub);
+  if (k >= (size_t)(src.nb >> sub)) return;
+  const size_t base = wl * src.nb + (k << sub);
   Pt acc = pt_identity_mont();
   bool have = false;
   for (int t = lane; t < (1 << sub); t += 32) {
-    Pt x = ld_pt(base + 32 * (size_t)t);
+    Pt x = load_bucket(src, base + t);
     if (!have) { acc = x; have = true; } else acc = pt_add_ni(acc, x);
   }
   acc = warp_sum_pt(acc);
@@ -423,14 +437,17 @@ __device__ __forceinline__ void warp_weighted(const uint32_t* __restrict__ items
 
 // stage 1: one block per (window, k2): 2^a1 warps x 32 lanes, one bucket per thread.
 //   pm1[blk][warp] = sum over lanes,  pm0[blk][lane] = sum over warps,  tot[blk] = sum of the block's buckets
-__global__ void __launch_bounds__(256) msm_cube1_kernel(const uint32_t* __restrict__ buckets, int a1, uint32_t* __restrict__ tot,
+// raw_mask: bit wl set = the buckets[] of local window wl (within the group) are final (written by msm_unfold_kernel).
+// Blocks are kept to 128 threads / <= 168 registers so that they fit next to the accumulation's resident blocks.
+__global__ void __launch_bounds__(128, 3) msm_cube1_kernel(BucketSrc src, uint32_t raw_mask, int a1, uint32_t* __restrict__ tot,
                                                         uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0) {
   extern __shared__ uint4 cube_sm[];           // [8 uint4 of a point][warp][lane]  +  [8][warp] row sums
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = 1 << a1;
   const size_t blk = blockIdx.x;
   uint4* colbuf = cube_sm;
   uint4* rowbuf = cube_sm + 8 * nw * 32;
-  Pt v = ld_pt(buckets + 32 * (blk * (size_t)(nw * 32) + threadIdx.x));
+  const size_t gidx = blk * (size_t)(nw * 32) + threadIdx.x;
+  Pt v = ((raw_mask >> (int)(gidx / src.nb)) & 1u) ? ld_pt(src.buckets + 32 * gidx) : load_bucket(src, gidx);
   auto put = [&](uint4* base, int stride, int idx, const Pt& p) {
     base[0 * stride + idx] = make_uint4(p.X.w[0], p.X.w[1], p.X.w[2], p.X.w[3]); base[1 * stride + idx] = make_uint4(p.X.w[4], p.X.w[5], p.X.w[6], p.X.w[7]);
     base[2 * stride + idx] = make_uint4(p.Y.w[0], p.Y.w[1], p.Y.w[2], p.Y.w[3]); base[3 * stride + idx] = make_uint4(p.Y.w[4], p.Y.w[5], p.Y.w[6], p.Y.w[7]);
@@ -499,7 +516,8 @@ __global__ void __launch_bounds__(128) msm_cube2a_kernel(const uint32_t* __restr
 
 // stage 2b: four warps per window: comp[0] = sum v M3[v], comp[1] = sum v M2[v], comp[2] = sum v M1[v],
 // comp[3] = sum (v+1) M0[v]
-__global__ void __launch_bounds__(128) msm_cube2b_kernel(const uint32_t* __restrict__ marg, int a1, int a2, int a3, uint32_t* __restrict__ comp) {
+// drop_wl: local window (within the launch) whose lane digit k0 is a sub-bucket index (weight (k >> A0) + 1), or -1
+__global__ void __launch_bounds__(128) msm_cube2b_kernel(const uint32_t* __restrict__ marg, int a1, int a2, int a3, int drop_wl, uint32_t* __restrict__ comp) {
   const int lane = threadIdx.x & 31, which = threadIdx.x >> 5;
   const int nw = 1 << a1, n2 = 1 << a2, n3 = 1 << a3, ntask = nw + 32 + n2 + n3;
   const size_t wl = blockIdx.x;
@@ -508,7 +526,10 @@ __global__ void __launch_bounds__(128) msm_cube2b_kernel(const uint32_t* __restr
   if (which == 0)      warp_weighted<1>(m + 32 * (nw + 32 + n2), n3, lane, total, weighted);
   else if (which == 1) warp_weighted<1>(m + 32 * (nw + 32), n2, lane, total, weighted);
   else if (which == 2) warp_weighted<1>(m, nw, lane, total, weighted);
-  else { warp_weighted<1>(m + 32 * nw, 32, lane, total, weighted); weighted = pt_add_ni(weighted, total); }
+  else {
+    warp_weighted<1>(m + 32 * nw, 32, lane, total, weighted);
+    weighted = ((int)wl == drop_wl) ? total : pt_add_ni(weighted, total);
+  }
   if (lane == 0) st_pt(comp + 32 * (wl * 4 + which), weighted);
 }
 
@@ -611,7 +632,8 @@ __device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
 //     acc += comp0;  acc = 2^a2 acc;  acc += comp1;  acc = 2^a1 acc;  acc += comp2;  acc = 2^A0 acc;  acc += comp3
 //   acc = 2^gap_post acc          (gap_post already excludes A0 + a1 + a2 when another group follows)
 // first != 0: acc starts as the identity.  out52 != nullptr: also store the result in the ABI layout.
-__global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ comp, int ng, int first, int a1, int a2,
+// drop0: the first window's comp3 carries weight 1 on every bucket (sub-bucketed short window): A0 - drop0 doublings.
+__global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ comp, int ng, int first, int a1, int a2, int drop0,
                                                        int gap_in, int gap_post, uint32_t* __restrict__ acc_io,
                                                        uint64_t* __restrict__ out52) {
   const int lane = threadIdx.x;
@@ -623,7 +645,7 @@ __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restric
     const uint32_t* cw = comp - 128 * (ptrdiff_t)i;          // windows in descending order
 #pragma unroll 1
     for (int part = 0; part < 4; part++) {
-      int nd = part == 0 ? (i > 0 ? gap_in - A0 - a1 - a2 : 0) : (part == 1 ? a2 : (part == 2 ? a1 : A0));
+      int nd = part == 0 ? (i > 0 ? gap_in - A0 - a1 - a2 : 0) : (part == 1 ? a2 : (part == 2 ? a1 : (i == 0 ? A0 - drop0 : A0)));
 #pragma unroll 1
       for (int j = 0; j < nd; j++) c = quad_double(c, q, qbase);
       c = quad_add(c, ld_pt(cw + 32 * part), q, qbase);
@@ -681,7 +703,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o_cursor = o; o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_buckets = o; o = align_up(o + (size_t)nwl * nb * 128, 256);
     const int bits = c - 1;                                     // nb = 2^bits, bits in 7..15
-    const int a1 = bits - A0 < 3 ? bits - A0 : 3;               // warps per cube block = 2^a1
+    const int a1 = 2;                                           // warps per cube block = 2^a1 (bits >= 7)
     const int ab = bits - A0 - a1;                              // block-index bits, split into k2 (a2) and k3 (a3)
     const int a2 = ab < 4 ? ab : 4, a3 = ab - a2;
     const int nblk = 1 << ab;                                   // cube blocks per window
@@ -721,8 +743,12 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     uint32_t *comp = (uint32_t*)(ws + o_comp);
     cudaStream_t st = ctx->stream;
     if (!ctx->side_stream) {
-      ZC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-      ZC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->chain_stream, cudaStreamNonBlocking));
+      // highest priority: the side kernels are small and latency-bound; their blocks must not queue behind the
+      // accumulation's grid (observed: 4x longer when they do, and the last group's tail waits for them)
+      int prio_lo = 0, prio_hi = 0;
+      ZC_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi));
+      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, prio_hi));
       for (int i = 0; i < 16; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     }
     // st: digits, sort, accumulation.  side: operand preparation, then stitch + reduce of each group.  chain: the
@@ -734,27 +760,36 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     // the call's arguments stay the same (repeated proofs over resident generators): one launch instead of a launch-
     // latency-bound sequence -- at 8 ranks the per-rank kernels are short enough for launch gaps to rival the math.
     uint64_t nlaunch = 0;
+    // ZC_MSM_TRACE=1: no graph, a timing event after every kernel, timeline printed to stderr (development aid)
+    static const bool trace = getenv("ZC_MSM_TRACE") != nullptr;
+    struct Mark { cudaEvent_t ev; const char* name; int stream; };
+    std::vector<Mark> marks;
+    auto mark = [&](cudaStream_t s_, int sid, const char* name) {
+      if (!trace) return;
+      cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); marks.push_back({e, name, sid});
+    };
     auto enqueue = [&]() -> int32_t {
+      mark(st, 0, "start");
       ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwl * nb * 4, st));
       ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
       ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
       ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[0], 0));
-      msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++;
+      msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++; mark(side, 1, "msm_prep_kernel");
       ZC_CUDA(ctx, cudaEventRecord(ctx->ev[1], side));
       {
         const unsigned grid = (unsigned)((n + 255) / 256);
         switch (c) {
-  #define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, rank, nranks, digits, hist); break;
+#define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, rank, nranks, digits, hist); break;
           ZC_DIGITS_CASE(8) ZC_DIGITS_CASE(9) ZC_DIGITS_CASE(10) ZC_DIGITS_CASE(11) ZC_DIGITS_CASE(12)
           ZC_DIGITS_CASE(13) ZC_DIGITS_CASE(14) ZC_DIGITS_CASE(15) ZC_DIGITS_CASE(16)
-  #undef ZC_DIGITS_CASE
+#undef ZC_DIGITS_CASE
         }
-        nlaunch++;
+        nlaunch++; mark(st, 0, "msm_digits_kernel");
       }
-      msm_scan_kernel<<<nwl, SCAN_TPB, 0, st>>>(hist, offs, cursor, nb); nlaunch++;
+      msm_scan_kernel<<<nwl, SCAN_TPB, 0, st>>>(hist, offs, cursor, nb); nlaunch++; mark(st, 0, "msm_scan_kernel");
       {
         size_t tot = n * (size_t)nwl;
-        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); nlaunch++;
+        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); nlaunch++; mark(st, 0, "msm_scatter_kernel");
       }
       // Window groups, top-down.  Local window wl is global window rank + nranks * wl.  After a group's buckets are
       // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
@@ -770,33 +805,40 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg), *g_partT = partT + 32 * ((size_t)lo * nseg);
         uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
         if (g == 0) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
-        msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, gsz, nb, g_buckets, g_partH, g_partT); nlaunch++;
+        msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, gsz, nb, g_buckets, g_partH, g_partT); nlaunch++; mark(st, 0, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
         ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
-        msm_fix_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, side>>>(g_offs, g_hist, nseg, gsz, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++;
-        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++;
-        for (int wl = lo; wl < hi; wl++) {                        // short (top) windows: sum sub-buckets back
+        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, side>>>(g_offs, g_hist, gsz, nb, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_fixq_kernel");
+        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_heavy_kernel");
+        const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb};
+        // A short (top) window spreads each digit over 2^sub sub-buckets.  sub == A0: the sub-bucket index is exactly the
+        // lane digit of the cube, which then simply carries weight 0 (drop).  Otherwise sum the sub-buckets back first.
+        uint32_t raw_mask = 0; int drop_wl = -1;
+        for (int wl = lo; wl < hi; wl++) {
           const int sub = short_window_sub_bits(c, rank + nranks * wl);
-          if (sub > 0) {
-            uint32_t *wb = buckets + 32 * ((size_t)wl * nb);
-            msm_fold_kernel<<<(unsigned)(((nb >> sub) + 3) / 4), 128, 0, side>>>(wb, nb, sub, folded); nlaunch++;
-            msm_unfold_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, side>>>(folded, nb, nb >> sub, wb); nlaunch++;
+          if (sub == A0 && g == 0 && wl == hi - 1) drop_wl = wl - lo;
+          else if (sub > 0) {
+            raw_mask |= 1u << (wl - lo);
+            msm_fold_kernel<<<(unsigned)(((nb >> sub) + 3) / 4), 128, 0, side>>>(src, (size_t)(wl - lo), sub, folded); nlaunch++; mark(side, 1, "msm_fold_kernel");
+            msm_unfold_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, side>>>(folded, nb, nb >> sub, buckets + 32 * ((size_t)wl * nb)); nlaunch++; mark(side, 1, "msm_unfold_kernel");
           }
         }
         const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
-        msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, side>>>(g_buckets, a1, btot + 32 * ((size_t)lo * nblk),
-            pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++;
+        msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, side>>>(src, raw_mask, a1, btot + 32 * ((size_t)lo * nblk),
+            pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(side, 1, "msm_cube1_kernel");
         msm_cube2a_kernel<<<(unsigned)(((size_t)gsz * ntask + 3) / 4), 128, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
             pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz,
-            marg + 32 * ((size_t)lo * ntask)); nlaunch++;
-        msm_cube2b_kernel<<<gsz, 128, 0, side>>>(marg + 32 * ((size_t)lo * ntask), a1, a2, a3, comp + 128 * (size_t)lo); nlaunch++;
+            marg + 32 * ((size_t)lo * ntask)); nlaunch++; mark(side, 1, "msm_cube2a_kernel");
+        msm_cube2b_kernel<<<gsz, 128, 0, side>>>(marg + 32 * ((size_t)lo * ntask), a1, a2, a3, drop_wl, comp + 128 * (size_t)lo); nlaunch++; mark(side, 1, "msm_cube2b_kernel");
+        // only the top local window of the whole MSM can be short, i.e. the first window of the first group
+        const int drop0 = (drop_wl == gsz - 1) ? A0 : 0;
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[6 + g], side));
         ZC_CUDA(ctx, cudaStreamWaitEvent(chain, ctx->ev[6 + g], 0));
         const bool last = (g == ngroups - 1);
-        msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, c * nranks,
-                                             last ? c * rank : c * nranks - A0 - a1 - a2, acc, last ? partial : nullptr); nlaunch++;
+        msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, drop0, c * nranks,
+                                             last ? c * rank : c * nranks - A0 - a1 - a2, acc, last ? partial : nullptr); nlaunch++; mark(chain, 2, "msm_chain_kernel");
         hi = lo;
       }
       ZC_CUDA(ctx, cudaEventRecord(ctx->ev[10], chain));
@@ -807,10 +849,19 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     const zc_msm_key key = {points, scalars, n, c, rank, nranks, 0, partial, ctx->msm_ws};
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     ZC_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
-    if (cap != cudaStreamCaptureStatusNone) {
+    if (cap != cudaStreamCaptureStatusNone || trace) {
       int32_t rc = enqueue();                                   // the caller is capturing: become part of their graph
       if (rc) return rc;
       ctx->launches += nlaunch;
+      if (trace && !marks.empty()) {
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[zc_msm trace] n=%zu c=%d rank %d/%d\n", n, c, rank, nranks);
+        for (size_t i = 1; i < marks.size(); i++) {
+          float ms = 0; cudaEventElapsedTime(&ms, marks[0].ev, marks[i].ev);
+          fprintf(stderr, "  %8.1f us  s%d  %s\n", ms * 1e3, marks[i].stream, marks[i].name);
+        }
+        for (auto& m : marks) cudaEventDestroy(m.ev);
+      }
     } else if (ctx->msm_graph_exec && memcmp(&key, &ctx->msm_key, sizeof(key)) == 0) {
       ZC_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)ctx->msm_graph_exec, st));
       ctx->launches += ctx->msm_graph_launches;
