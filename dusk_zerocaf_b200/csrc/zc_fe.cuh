@@ -338,6 +338,141 @@ __device__ __forceinline__ void mul_wide_8x8(uint32_t (&t)[16], const uint32_t (
         "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]));
 }
 
+// t[0..15] = a^2: 28 cross products (rows below, same split-accumulator scheme as mul_wide_8x8), doubled, plus the 8
+// squares a_i^2 -- 36 wide multiplies instead of 64.
+__device__ __forceinline__ void sqr_wide_8(uint32_t (&t)[16], const uint32_t (&a)[8]) {
+  uint32_t ev[14], od[14];          // cross terms: ev[2..13] at offsets 2..13, od[k] at offset k+1
+#define ZC_MULW(LO, HI, X, Y) asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(LO), "=r"(HI) : "r"(X), "r"(Y))
+  // row 0: a[0] * a[1..7], all fresh
+  ZC_MULW(od[0], od[1], a[1], a[0]); ZC_MULW(ev[2], ev[3], a[2], a[0]); ZC_MULW(od[2], od[3], a[3], a[0]);
+  ZC_MULW(ev[4], ev[5], a[4], a[0]); ZC_MULW(od[4], od[5], a[5], a[0]); ZC_MULW(ev[6], ev[7], a[6], a[0]);
+  ZC_MULW(od[6], od[7], a[7], a[0]);
+  // row 1: a[1] * a[2..7]
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %13, %18, %0;\n\t"
+      "madc.hi.cc.u32  %1, %13, %18, %1;\n\t"
+      "madc.lo.cc.u32  %2, %15, %18, %2;\n\t"
+      "madc.hi.cc.u32  %3, %15, %18, %3;\n\t"
+      "madc.lo.cc.u32  %4, %17, %18, 0;\n\t"
+      "madc.hi.u32     %5, %17, %18, 0;\n\t"
+      "mad.lo.cc.u32   %6, %12, %18, %6;\n\t"
+      "madc.hi.cc.u32  %7, %12, %18, %7;\n\t"
+      "madc.lo.cc.u32  %8, %14, %18, %8;\n\t"
+      "madc.hi.cc.u32  %9, %14, %18, %9;\n\t"
+      "madc.lo.cc.u32  %10, %16, %18, %10;\n\t"
+      "madc.hi.cc.u32  %11, %16, %18, %11;\n\t"
+      "addc.u32        %5, %5, 0;\n\t"
+      "}"
+      : "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "=&r"(ev[8]), "=&r"(ev[9]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[1]));
+  // row 2: a[2] * a[3..7]
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %10, %15, %0;\n\t"
+      "madc.hi.cc.u32  %1, %10, %15, %1;\n\t"
+      "madc.lo.cc.u32  %2, %12, %15, %2;\n\t"
+      "madc.hi.cc.u32  %3, %12, %15, %3;\n\t"
+      "madc.lo.cc.u32  %4, %14, %15, 0;\n\t"
+      "madc.hi.u32     %5, %14, %15, 0;\n\t"
+      "mad.lo.cc.u32   %6, %11, %15, %6;\n\t"
+      "madc.hi.cc.u32  %7, %11, %15, %7;\n\t"
+      "madc.lo.cc.u32  %8, %13, %15, %8;\n\t"
+      "madc.hi.cc.u32  %9, %13, %15, %9;\n\t"
+      "addc.u32        %5, %5, 0;\n\t"
+      "}"
+      : "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "=&r"(od[8]), "=&r"(od[9]), "+r"(ev[6]), "+r"(ev[7]), "+r"(ev[8]), "+r"(ev[9])
+      : "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[2]));
+  // row 3: a[3] * a[4..7]
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %9, %12, %0;\n\t"
+      "madc.hi.cc.u32  %1, %9, %12, %1;\n\t"
+      "madc.lo.cc.u32  %2, %11, %12, 0;\n\t"
+      "madc.hi.u32     %3, %11, %12, 0;\n\t"
+      "mad.lo.cc.u32   %4, %8, %12, %4;\n\t"
+      "madc.hi.cc.u32  %5, %8, %12, %5;\n\t"
+      "madc.lo.cc.u32  %6, %10, %12, %6;\n\t"
+      "madc.hi.cc.u32  %7, %10, %12, %7;\n\t"
+      "addc.u32        %3, %3, 0;\n\t"
+      "}"
+      : "+r"(ev[8]), "+r"(ev[9]), "=&r"(ev[10]), "=&r"(ev[11]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "+r"(od[9])
+      : "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[3]));
+  // row 4: a[4] * a[5..7]
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %6, %9, %0;\n\t"
+      "madc.hi.cc.u32  %1, %6, %9, %1;\n\t"
+      "madc.lo.cc.u32  %2, %8, %9, 0;\n\t"
+      "madc.hi.u32     %3, %8, %9, 0;\n\t"
+      "mad.lo.cc.u32   %4, %7, %9, %4;\n\t"
+      "madc.hi.cc.u32  %5, %7, %9, %5;\n\t"
+      "addc.u32        %3, %3, 0;\n\t"
+      "}"
+      : "+r"(od[8]), "+r"(od[9]), "=&r"(od[10]), "=&r"(od[11]), "+r"(ev[10]), "+r"(ev[11])
+      : "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[4]));
+  // row 5: a[5] * a[6..7]
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %5, %6, 0;\n\t"
+      "madc.hi.u32     %1, %5, %6, 0;\n\t"
+      "mad.lo.cc.u32   %2, %4, %6, %2;\n\t"
+      "madc.hi.cc.u32  %3, %4, %6, %3;\n\t"
+      "addc.u32        %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(ev[12]), "=&r"(ev[13]), "+r"(od[10]), "+r"(od[11])
+      : "r"(a[6]), "r"(a[7]), "r"(a[5]));
+  // row 6: a[6] * a[7..7]
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %2, %3, 0;\n\t"
+      "madc.hi.u32     %1, %2, %3, 0;\n\t"
+      "}"
+      : "=&r"(od[12]), "=&r"(od[13])
+      : "r"(a[7]), "r"(a[6]));
+  // the squares
+#pragma unroll
+  for (int i = 0; i < 8; i++) ZC_MULW(t[2 * i], t[2 * i + 1], a[i], a[i]);
+#undef ZC_MULW
+  // c = ev + (od << 32): c[1] = od[0], c[k] = ev[k] + od[k-1] (k = 2..13), c[14] = od[13] + carry   (reuses od[])
+  asm("add.cc.u32  %0, %0, %13;\n\t"
+      "addc.cc.u32 %1, %1, %14;\n\t"
+      "addc.cc.u32 %2, %2, %15;\n\t"
+      "addc.cc.u32 %3, %3, %16;\n\t"
+      "addc.cc.u32 %4, %4, %17;\n\t"
+      "addc.cc.u32 %5, %5, %18;\n\t"
+      "addc.cc.u32 %6, %6, %19;\n\t"
+      "addc.cc.u32 %7, %7, %20;\n\t"
+      "addc.cc.u32 %8, %8, %21;\n\t"
+      "addc.cc.u32 %9, %9, %22;\n\t"
+      "addc.cc.u32 %10, %10, %23;\n\t"
+      "addc.cc.u32 %11, %11, %24;\n\t"
+      "addc.u32    %12, %12, 0;\n\t"
+      : "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "+r"(od[9]),
+        "+r"(od[10]), "+r"(od[11]), "+r"(od[12]), "+r"(od[13])
+      : "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]),
+        "r"(ev[11]), "r"(ev[12]), "r"(ev[13]));
+  // now c[k] = od[k-1] for k = 1..14.  t += 2 c
+  uint32_t d[15];                   // d[k-1] = word k of 2c, k = 1..15
+  d[0] = od[0] << 1;
+#pragma unroll
+  for (int k = 2; k <= 14; k++) d[k - 1] = __funnelshift_l(od[k - 2], od[k - 1], 1);
+  d[14] = od[13] >> 31;
+  asm("add.cc.u32  %0, %0, %15;\n\t"
+      "addc.cc.u32 %1, %1, %16;\n\t"
+      "addc.cc.u32 %2, %2, %17;\n\t"
+      "addc.cc.u32 %3, %3, %18;\n\t"
+      "addc.cc.u32 %4, %4, %19;\n\t"
+      "addc.cc.u32 %5, %5, %20;\n\t"
+      "addc.cc.u32 %6, %6, %21;\n\t"
+      "addc.cc.u32 %7, %7, %22;\n\t"
+      "addc.cc.u32 %8, %8, %23;\n\t"
+      "addc.cc.u32 %9, %9, %24;\n\t"
+      "addc.cc.u32 %10, %10, %25;\n\t"
+      "addc.cc.u32 %11, %11, %26;\n\t"
+      "addc.cc.u32 %12, %12, %27;\n\t"
+      "addc.cc.u32 %13, %13, %28;\n\t"
+      "addc.u32    %14, %14, %29;\n\t"
+      : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]),
+        "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+      : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]), "r"(d[8]), "r"(d[9]),
+        "r"(d[10]), "r"(d[11]), "r"(d[12]), "r"(d[13]), "r"(d[14]));
+}
+
 // u[0..11] = c * h   (c = the modulus' four low words, h 8 words; 32 wide multiplies)
 template <class M>
 __device__ __forceinline__ void mul_c_8(uint32_t (&u)[12], const uint32_t (&h)[8]) {
@@ -415,23 +550,24 @@ __device__ __forceinline__ void shl_words(uint32_t (&r)[8], const Fe& a) {
   for (int k = 1; k < 8; k++) r[k] = __funnelshift_l(a.w[k - 1], a.w[k], S);
 }
 
-// fold a 16-word product t = 2^(256-K) * x (x < m^2) to x mod m, canonical
-template <class M>
+// fold a 16-word product t = 2^S * x (x < m^2, S <= 256 - K) to x mod m, canonical
+template <class M, int S>
 __device__ __forceinline__ Fe fold_product(const uint32_t (&t)[16]) {
-  constexpr int S = Shape<M>::S, TOP = M::TOP;
+  constexpr int TOP = M::TOP, K = Shape<M>::K, HS = K + S - 224;     // H = t >> (K + S) starts HS bits into word 7
   uint32_t h[8], u[12], g[4], v[8];
+  static_assert(HS >= 1 && HS <= 32, "product shift out of range");
 #pragma unroll
-  for (int k = 0; k < 8; k++) h[k] = t[8 + k];
+  for (int k = 0; k < 8; k++) h[k] = (HS == 32) ? t[8 + k] : __funnelshift_r(t[7 + k], k + 8 < 16 ? t[8 + k] : 0u, HS);
   mul_c_8<M>(u, h);
   // Uh = u >> K  (K = 224 + TOP)
 #pragma unroll
   for (int k = 0; k < 4; k++) g[k] = __funnelshift_r(u[7 + k], u[8 + k], TOP);
   mul_c_4<M>(v, g);
-  // Lo = t[0..7] >> S
+  // Lo = (t mod 2^(K+S)) >> S
   Fe r;
 #pragma unroll
   for (int k = 0; k < 7; k++) r.w[k] = __funnelshift_r(t[k], t[k + 1], S);
-  r.w[7] = t[7] >> S;
+  r.w[7] = (HS == 32) ? (t[7] >> S) : ((t[7] & ((1u << HS) - 1u)) >> S);
   const uint32_t ul7 = u[7] & ((1u << TOP) - 1u);
   uint32_t bw;
   // r = Lo + V - Ul ; bw = all-ones when the result is negative
@@ -476,11 +612,16 @@ __device__ __forceinline__ Fe fe_mul_normal(const Fe& a, const Fe& b) {
   shl_words<Shape<M>::SA>(as, a);
   shl_words<Shape<M>::SB>(bs, b);
   mul_wide_8x8(t, as, bs);
-  return fold_product<M>(t);
+  return fold_product<M, Shape<M>::S>(t);
 }
 // a^2 mod m (field.rs:302-315 / scalar.rs:272-283 as a value)
 template <class M>
-__device__ __forceinline__ Fe fe_sqr_normal(const Fe& a) { return fe_mul_normal<M>(a, a); }
+__device__ __forceinline__ Fe fe_sqr_normal(const Fe& a) {
+  uint32_t as[8], t[16];
+  shl_words<Shape<M>::SA>(as, a);
+  sqr_wide_8(t, as);                       // 2^(2 SA) a^2
+  return fold_product<M, 2 * Shape<M>::SA>(t);
+}
 
 // ---- radix-2^52 limbs (the reference's [u64;5], field.rs:31-32) <-> 8 x u32 --------------------------
 __device__ __forceinline__ Fe fe_from_limbs52(uint64_t l0, uint64_t l1, uint64_t l2, uint64_t l3, uint64_t l4) {
