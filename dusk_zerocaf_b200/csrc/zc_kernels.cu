@@ -121,91 +121,92 @@ __global__ void __launch_bounds__(128) scalar_mul_strict_kernel(const uint64_t* 
   if (live) pt_store52(out + 20 * i, pt_from_mont(Q));
 }
 
-// ---- K3 fast: signed 4-bit fixed window, dedicated doubling, table of cached multiples in shared memory --------
-// digits d_j in [-8, 8), s = sum d_j 16^j; table holds 1P..8P in cached form; 63 windows cover 252 bits (s < L < 2^250).
-constexpr int SM_FAST_TPB = 64;
-__global__ void __launch_bounds__(SM_FAST_TPB) scalar_mul_fast_kernel(const uint64_t* __restrict__ points,
-                                                                      const uint64_t* __restrict__ scalars,
-                                                                      uint64_t* __restrict__ out, size_t n) {
-  // table[e][word-slot][thread]: conflict-free, each thread only touches its own column
-  extern __shared__ uint32_t tbl[];   // 8 entries * 32 words * SM_FAST_TPB threads
-  size_t i = (size_t)blockIdx.x * SM_FAST_TPB + threadIdx.x;
-  const bool live = i < n;
-  size_t ii = live ? i : 0;
-  const int tx = threadIdx.x;
-  Pt P = pt_to_mont(pt_load52(points + 20 * ii));
-  Fe s = fe_load52(scalars + 5 * ii);
-
+// ---- K3 fast: signed 4-bit fixed window, dedicated doubling, per-thread table of cached multiples in global scratch ----
+// digits d_j in [-8, 8), s = sum d_j 16^j; the table holds 1P..8P in cached form (Y+X, Y-X, Z, 2dT); 63 windows cover
+// 252 bits (s < L < 2^250).  The table (8 x 128 B per point) lives in a grow-only scratch arena indexed by the thread's
+// slot in the (persistent) grid, laid out [entry][16-byte word][slot] so that every table access of a warp is one
+// coalesced 512-byte transaction and mostly an L2 hit.  Keeping it out of shared memory leaves the kernel limited by
+// registers only (4 blocks of 128 threads per SM instead of 3 blocks of 64), which is what the dependent multiply chains
+// need to keep the integer pipe busy.
+constexpr int SM_FAST_TPB = 128;
+__global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const uint64_t* __restrict__ points,
+                                                                         const uint64_t* __restrict__ scalars,
+                                                                         uint64_t* __restrict__ out, size_t n,
+                                                                         uint4* __restrict__ table, size_t nslots) {
+  const size_t slot = (size_t)blockIdx.x * SM_FAST_TPB + threadIdx.x;
   auto store_entry = [&](int e, const PtCached& c) {
-    uint32_t* base = tbl + (size_t)e * 32 * SM_FAST_TPB + tx;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      base[(k) * SM_FAST_TPB] = c.YpX.w[k];
-      base[(8 + k) * SM_FAST_TPB] = c.YmX.w[k];
-      base[(16 + k) * SM_FAST_TPB] = c.Z.w[k];
-      base[(24 + k) * SM_FAST_TPB] = c.T2d.w[k];
-    }
+    uint4* base = table + (size_t)e * 8 * nslots + slot;
+    base[0 * nslots] = make_uint4(c.YpX.w[0], c.YpX.w[1], c.YpX.w[2], c.YpX.w[3]); base[1 * nslots] = make_uint4(c.YpX.w[4], c.YpX.w[5], c.YpX.w[6], c.YpX.w[7]);
+    base[2 * nslots] = make_uint4(c.YmX.w[0], c.YmX.w[1], c.YmX.w[2], c.YmX.w[3]); base[3 * nslots] = make_uint4(c.YmX.w[4], c.YmX.w[5], c.YmX.w[6], c.YmX.w[7]);
+    base[4 * nslots] = make_uint4(c.Z.w[0], c.Z.w[1], c.Z.w[2], c.Z.w[3]);         base[5 * nslots] = make_uint4(c.Z.w[4], c.Z.w[5], c.Z.w[6], c.Z.w[7]);
+    base[6 * nslots] = make_uint4(c.T2d.w[0], c.T2d.w[1], c.T2d.w[2], c.T2d.w[3]); base[7 * nslots] = make_uint4(c.T2d.w[4], c.T2d.w[5], c.T2d.w[6], c.T2d.w[7]);
+  };
+  auto load_fe = [&](const uint4* p, Fe& f) {
+    uint4 lo = p[0], hi = p[nslots];
+    f.w[0] = lo.x; f.w[1] = lo.y; f.w[2] = lo.z; f.w[3] = lo.w; f.w[4] = hi.x; f.w[5] = hi.y; f.w[6] = hi.z; f.w[7] = hi.w;
   };
   auto load_entry = [&](int e) {
     PtCached c;
-    const uint32_t* base = tbl + (size_t)e * 32 * SM_FAST_TPB + tx;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      c.YpX.w[k] = base[(k) * SM_FAST_TPB];
-      c.YmX.w[k] = base[(8 + k) * SM_FAST_TPB];
-      c.Z.w[k] = base[(16 + k) * SM_FAST_TPB];
-      c.T2d.w[k] = base[(24 + k) * SM_FAST_TPB];
-    }
+    const uint4* base = table + (size_t)e * 8 * nslots + slot;
+    load_fe(base, c.YpX); load_fe(base + 2 * nslots, c.YmX); load_fe(base + 4 * nslots, c.Z); load_fe(base + 6 * nslots, c.T2d);
     return c;
   };
-
-  {  // table: e -> (e+1) P
-    PtCached c1 = pt_to_cached(P);
-    store_entry(0, c1);
-    Pt acc = P;
+  for (size_t i = slot; ; i += nslots) {
+    // whole warps leave together (the loop body uses warp votes)
+    if (!__any_sync(0xffffffffu, i < n)) break;
+    const bool live = i < n;
+    const size_t ii = live ? i : 0;
+    Pt P = pt_to_mont(pt_load52(points + 20 * ii));
+    Fe s = fe_load52(scalars + 5 * ii);
+    {  // table: e -> (e+1) P
+      PtCached c1 = pt_to_cached(P);
+      store_entry(0, c1);
+      Pt acc = P;
 #pragma unroll 1
-    for (int e = 1; e < 8; e++) {
-      acc = pt_add_cached(acc, c1);
-      store_entry(e, pt_to_cached(acc));
-    }
-  }
-
-  // signed digits, most significant first.  carry-propagating recode done on the fly from the top is awkward, so
-  // recode from the bottom into a packed 4-bit array (63 digits + final carry digit).
-  uint32_t dig[8];   // 64 nibbles, two's-complement 4-bit digits
-  {
-    uint32_t carry = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      uint32_t w = s.w[k], o = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        uint32_t d = ((w >> (4 * j)) & 15u) + carry;   // 0..16
-        carry = (d >= 8u) ? 1u : 0u;                   // d in [8,16] -> d - 16, carry 1
-        o |= (d & 15u) << (4 * j);
+      for (int e = 1; e < 8; e++) {
+        acc = pt_add_cached(acc, c1);
+        store_entry(e, pt_to_cached(acc));
       }
-      dig[k] = o;
     }
-    // s < 2^250 so the top nibble (bits 252..255) is 0 before the carry and the final carry is always 0
-  }
-
-  Pt Q = pt_identity_mont();
+    // signed digits: recode from the bottom into a packed 4-bit array (two's-complement nibbles)
+    uint32_t dig[8];
+    {
+      uint32_t carry = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        uint32_t w = s.w[k], o = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          uint32_t d = ((w >> (4 * j)) & 15u) + carry;   // 0..16
+          carry = (d >= 8u) ? 1u : 0u;                   // d in [8,16] -> d - 16, carry 1
+          o |= (d & 15u) << (4 * j);
+        }
+        dig[k] = o;
+      }
+      // s < 2^250 so the top nibble (bits 252..255) is 0 before the carry and the final carry is always 0
+    }
+    Pt Q = pt_identity_mont();
 #pragma unroll 1
-  for (int j = 63; j >= 0; j--) {
-    if (j != 63) {
-      Q = pt_double_fast(Q); Q = pt_double_fast(Q); Q = pt_double_fast(Q); Q = pt_double_fast(Q);
+    for (int j = 63; j >= 0; j--) {
+      if (j != 63) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) Q = pt_double_fast(Q);
+      }
+      uint32_t nib = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) if ((j >> 3) == k) nib = dig[k];
+      nib = (nib >> (4 * (j & 7))) & 15u;
+      const int d = (nib >= 8u) ? (int)nib - 16 : (int)nib;
+      const int mag = d < 0 ? -d : d;
+      if (__any_sync(0xffffffffu, mag != 0)) {
+        PtCached c = load_entry(mag ? mag - 1 : 0);
+        if (d < 0) c = pt_cached_neg(c);
+        Pt r = pt_add_cached(Q, c);
+        if (mag != 0) Q = r;
+      }
     }
-    uint32_t nib = (dig[j >> 3] >> (4 * (j & 7))) & 15u;
-    int d = (nib >= 8u) ? (int)nib - 16 : (int)nib;
-    int mag = d < 0 ? -d : d;
-    if (__any_sync(0xffffffffu, mag != 0)) {
-      PtCached c = load_entry(mag ? mag - 1 : 0);
-      if (d < 0) c = pt_cached_neg(c);
-      Pt r = pt_add_cached(Q, c);
-      if (mag != 0) Q = r;
-    }
+    if (live) pt_store52(out + 20 * i, pt_from_mont(Q));
   }
-  if (live) pt_store52(out + 20 * i, pt_from_mont(Q));
 }
 
 // ---- fold k points in index order with the reference Add (one thread; k is the number of ranks) ---------------
@@ -331,7 +332,6 @@ int32_t zc_ctx_create(int32_t device, void* stream, zc_ctx** out) {
     if (e != cudaSuccess) { delete ctx; return -(int32_t)e; }
     ctx->own_stream = true;
   }
-  cudaFuncSetAttribute(scalar_mul_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * SM_FAST_TPB * 4);
   *out = ctx;
   return ZC_OK;
 }
@@ -508,7 +508,15 @@ int32_t zc_point_scalar_mul_batch_dev(zc_ctx* ctx, const uint64_t* points, const
   if (mode == ZC_SCALAR_MUL_STRICT) {
     scalar_mul_strict_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(points, scalars, out, n);
   } else {
-    scalar_mul_fast_kernel<<<grid_for(n, SM_FAST_TPB), SM_FAST_TPB, 8 * 32 * SM_FAST_TPB * 4, ctx->stream>>>(points, scalars, out, n);
+    // persistent grid: 4 blocks per SM; table arena = one 1 KB table per resident thread
+    unsigned grid = grid_for(n, SM_FAST_TPB);
+    const unsigned max_grid = 4u * (unsigned)ctx->sm_count;
+    if (grid > max_grid) grid = max_grid;
+    const size_t nslots = (size_t)grid * SM_FAST_TPB;
+    void* table = nullptr;
+    int32_t rc = zc_scratch(ctx, 5, nslots * 1024, &table);
+    if (rc) return rc;
+    scalar_mul_fast_kernel<<<grid, SM_FAST_TPB, 0, ctx->stream>>>(points, scalars, out, n, (uint4*)table, nslots);
   }
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
