@@ -77,6 +77,8 @@ def lib():
         getattr(L, f"zc_point_scalar_mul_batch{suf}").argtypes = [vp, vp, vp, vp, sz, i32]
         getattr(L, f"zc_ristretto_eq_batch{suf}").argtypes = [vp, vp, vp, vp, sz]
         getattr(L, f"zc_msm{suf}").argtypes = [vp, vp, vp, sz, i32, vp]
+        for nm in ("zc_fe_invert_batch", "zc_point_to_affine_batch", "zc_ristretto_compress_batch"):
+            getattr(L, nm + suf).argtypes = [vp, vp, vp, sz]
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
     L.zc_msm_partial_dev.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
     L.zc_point_fold_dev.argtypes = [vp, vp, sz, vp]

@@ -77,6 +77,29 @@ def ristretto_eq(p, q, ctx=None):
     return out
 
 
+def fe_invert(a, ctx=None):
+    """FieldElement::inverse (field.rs:854-925); inverse(0) = 0 here, the reference panics."""
+    return _un("zc_fe_invert_batch", a, 5, ctx)
+
+
+def point_to_affine(p, ctx=None):
+    """AffinePoint::from(EdwardsPoint) (edwards.rs:1085-1092): (n, 10) limbs = x | y."""
+    ctx = ctx or default_context()
+    p = _arr(p, 20)
+    out = np.empty((p.shape[0], 10), dtype=np.uint64)
+    ctx.call("zc_point_to_affine_batch", p, out, p.shape[0])
+    return out
+
+
+def ristretto_compress(p, ctx=None):
+    """RistrettoPoint::compress (ristretto.rs:398-425): (n, 32) uint8."""
+    ctx = ctx or default_context()
+    p = _arr(p, 20)
+    out = np.empty((p.shape[0], 32), dtype=np.uint8)
+    ctx.call("zc_ristretto_compress_batch", p, out, p.shape[0])
+    return out
+
+
 def msm(points, scalars, window_bits=16, ctx=None):
     """sum_i [s_i] P_i as an EdwardsPoint (20 limbs); a group element, compare canonically."""
     ctx = ctx or default_context()

@@ -1,0 +1,200 @@
+// zc_encode.cu -- batched canonicalisation of points: the wire-format step right after the hot path.
+//
+//   zc_fe_invert_batch          FieldElement::inverse               /root/reference/src/backend/u64/field.rs:854-925
+//   zc_point_to_affine_batch    AffinePoint::from(EdwardsPoint)     /root/reference/src/edwards.rs:1085-1092
+//   zc_ristretto_compress_batch RistrettoPoint::compress            /root/reference/src/ristretto.rs:398-425
+//                               (inv_sqrt / sqrt_ratio_i field.rs:443-503, is_positive :552-557, to_bytes :591-631)
+//
+// The reference computes these with data-dependent loops (Savas-Koc almost-Montgomery inverse, Tonelli-Shanks); every
+// one of them returns a uniquely defined VALUE (the inverse; the non-negative root), so the device code evaluates the
+// same values with fixed exponent chains -- a^(p-2) and the p = 5 (mod 8) square-root-ratio recipe with exponent
+// (p-5)/8 -- which keep all 32 lanes of a warp in lockstep.  Outputs are bit-identical to the reference's.
+#include "zc_internal.h"
+#include "zc_point.cuh"
+
+using namespace zc;
+
+namespace {
+
+constexpr int TPB = 128;
+
+// exponents as little-endian 32-bit words (uniform across threads: plain square-and-multiply, no divergence)
+__constant__ uint32_t E_INV[8]  = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};   // p - 2      (253 bits)
+__constant__ uint32_t E_SQRT[8] = {0x4b9eba7du, 0xcb024c63u, 0xd45ef39au, 0x029bdf3bu, 0u, 0u, 0u, 0x02000000u};   // (p - 5)/8  (250 bits)
+
+__device__ __forceinline__ Fe SQRT_M1_MONT()      { return Fe{{0xa8c6c570u, 0xdb9954e7u, 0xfb49700du, 0xc85212d7u, 0x6de88652u, 0x28c7dc33u, 0x76c0a9d5u, 0x0aa666a6u}}; }   // constants.rs:96-102
+__device__ __forceinline__ Fe INVSQRT_AMD_MONT()  { return Fe{{0x9c6a4e67u, 0xf2915c70u, 0x5445ce4du, 0x1200721bu, 0x86e004e5u, 0x4500326au, 0x2a9217d4u, 0x05b18190u}}; }   // constants.rs:123-129
+__device__ __forceinline__ Fe MINUS_ONE_MONT()    { return Fe{{0xcf5d3ed0u, 0x812631a5u, 0x2f79cd65u, 0x4def9deau, 0x00000001u, 0u, 0u, 0u}}; }
+__device__ __forceinline__ Fe POS_RANGE()         { return Fe{{0x2e7ae9f6u, 0x2c09318du, 0x517bce6bu, 0x0a6f7cefu, 0u, 0u, 0u, 0x08000000u}}; }   // (p-1)/2, constants.rs:12-13
+
+// Out of line: the exponent loops call these ~315 times; one copy keeps the kernels small.
+__device__ __noinline__ Fe mul_ni(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
+
+// a^e for a Montgomery-form a and a constant exponent whose top set bit is bit nbits-1
+__device__ __forceinline__ Fe fe_pow_const(const Fe& a, const uint32_t* __restrict__ e, int nbits) {
+  Fe r = a;
+#pragma unroll 1
+  for (int bit = nbits - 2; bit >= 0; bit--) {
+    r = mul_ni(r, r);
+    if ((e[bit >> 5] >> (bit & 31)) & 1u) r = mul_ni(r, a);
+  }
+  return r;
+}
+
+// x <= (p-1)/2 for a canonical NORMAL-form x                       field.rs:552-557
+__device__ __forceinline__ bool fe_is_positive(const Fe& x) {
+  const Fe pr = POS_RANGE();
+  uint32_t bw;
+  asm("sub.cc.u32  %0, %1, %9;\n\t"
+      "subc.cc.u32 %0, %2, %10;\n\t"
+      "subc.cc.u32 %0, %3, %11;\n\t"
+      "subc.cc.u32 %0, %4, %12;\n\t"
+      "subc.cc.u32 %0, %5, %13;\n\t"
+      "subc.cc.u32 %0, %6, %14;\n\t"
+      "subc.cc.u32 %0, %7, %15;\n\t"
+      "subc.cc.u32 %0, %8, %16;\n\t"
+      "subc.u32    %0, 0, 0;\n\t"
+      : "=&r"(bw)
+      : "r"(pr.w[0]), "r"(pr.w[1]), "r"(pr.w[2]), "r"(pr.w[3]), "r"(pr.w[4]), "r"(pr.w[5]), "r"(pr.w[6]), "r"(pr.w[7]),
+        "r"(x.w[0]), "r"(x.w[1]), "r"(x.w[2]), "r"(x.w[3]), "r"(x.w[4]), "r"(x.w[5]), "r"(x.w[6]), "r"(x.w[7]));
+  return bw == 0;            // no borrow: POS_RANGE - x >= 0
+}
+// positivity of a Montgomery-form value (the predicate is defined on the value itself)
+__device__ __forceinline__ bool mont_is_positive(const Fe& xm) { return fe_is_positive(from_mont<ModP>(xm)); }
+
+// (was_square, +sqrt(1/v)) or (0, +sqrt(i/v)); v = 0 -> (0, 0).  Montgomery form in and out.     field.rs:443-503
+__device__ __forceinline__ Fe mont_inv_sqrt(const Fe& v) {
+  typedef ModP M;
+  const Fe one = Consts<M>::R1(), i = SQRT_M1_MONT();
+  Fe v2 = mul_ni(v, v);
+  Fe v3 = mul_ni(v2, v);
+  Fe v7 = mul_ni(mul_ni(v3, v3), v);
+  Fe r = mul_ni(v3, fe_pow_const(v7, E_SQRT, 250));
+  Fe check = mul_ni(v, mul_ni(r, r));
+  // check is one of 1, -1 (r <- i r), -i (r <- i r, non-square), i (non-square); 0 when v = 0 (r = 0 already)
+  const bool flip = fe_eq(check, MINUS_ONE_MONT()) || fe_eq(check, fe_neg<M>(i));
+  Fe ri = mul_ni(r, i);
+  if (flip) r = ri;
+  if (!mont_is_positive(r)) r = fe_neg<M>(r);
+  (void)one;
+  return r;
+}
+
+__global__ void __launch_bounds__(TPB) fe_invert_kernel(const uint64_t* __restrict__ a, uint64_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  Fe x = to_mont<ModP>(fe_load52(a + 5 * i));
+  fe_store52(out + 5 * i, from_mont<ModP>(fe_pow_const(x, E_INV, 253)));
+}
+
+// (x, y) = (X / Z, Y / Z)                                                                        edwards.rs:1085-1092
+__global__ void __launch_bounds__(TPB) pt_to_affine_kernel(const uint64_t* __restrict__ p, uint64_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  Fe X = fe_load52(p + 20 * i), Y = fe_load52(p + 20 * i + 5);
+  Fe zinv = fe_pow_const(to_mont<ModP>(fe_load52(p + 20 * i + 10)), E_INV, 253);   // Z^-1 R
+  fe_store52(out + 10 * i, mul_ni(X, zinv));           // normal * Montgomery -> normal
+  fe_store52(out + 10 * i + 5, mul_ni(Y, zinv));
+}
+
+// Ristretto encoding                                                                             ristretto.rs:398-425
+__global__ void __launch_bounds__(TPB) ristretto_compress_kernel(const uint64_t* __restrict__ p, uint8_t* __restrict__ out, size_t n) {
+  typedef ModP M;
+  size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (idx >= n) return;
+  Pt P = pt_to_mont(pt_load52(p + 20 * idx));
+  const Fe i = SQRT_M1_MONT();
+  Fe u1 = mul_ni(fe_add<M>(P.Z, P.Y), fe_sub<M>(P.Z, P.Y));
+  Fe u2 = mul_ni(P.X, P.Y);
+  Fe I = mont_inv_sqrt(mul_ni(u1, mul_ni(u2, u2)));
+  Fe D1 = mul_ni(u1, I);
+  Fe D2 = mul_ni(u2, I);
+  Fe Zinv = mul_ni(mul_ni(D1, D2), P.T);
+  Fe x = P.X, y = P.Y, D = D2;
+  if (!mont_is_positive(mul_ni(P.T, Zinv))) {
+    x = mul_ni(i, P.Y);
+    y = mul_ni(i, P.X);
+    D = mul_ni(D1, INVSQRT_AMD_MONT());
+  }
+  if (!mont_is_positive(mul_ni(x, Zinv))) y = fe_neg<M>(y);
+  Fe s = from_mont<M>(mul_ni(fe_sub<M>(P.Z, y), D));
+  if (!fe_is_positive(s)) s = fe_neg<M>(s);
+  // to_bytes: the canonical value, little-endian (field.rs:591-631)
+  uint4* o = reinterpret_cast<uint4*>(out + 32 * idx);
+  o[0] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+  o[1] = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+}
+
+inline unsigned grid_for(size_t n) { return (unsigned)((n + TPB - 1) / TPB); }
+constexpr size_t MAX_N = (size_t)1 << 31;
+
+// small synchronous host wrapper (these are not bandwidth-bound: ~320 multiplications per element)
+template <class F>
+int32_t host_unary(zc_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes, F run) {
+  void *din = nullptr, *dout = nullptr;
+  int32_t rc;
+  if ((rc = zc_scratch(ctx, 0, in_bytes, &din))) return rc;
+  if ((rc = zc_scratch(ctx, 2, out_bytes, &dout))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = run(din, dout))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZC_OK;
+}
+
+}  // namespace
+
+#define ZC_ENC_PROLOGUE(ctx, n, cond)                                                           \
+  do {                                                                                          \
+    if (!(ctx)) return ZC_ERR_NULL;                                                             \
+    ZC_CUDA(ctx, cudaSetDevice((ctx)->device));                                                 \
+    if ((n) > MAX_N) return zc_fail(ctx, ZC_ERR_SIZE, "n exceeds 2^31");                        \
+    if ((n) == 0) return ZC_OK;                                                                 \
+    if (!(cond)) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");                     \
+  } while (0)
+
+extern "C" {
+
+int32_t zc_fe_invert_batch_dev(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, a && out);
+  fe_invert_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(a, out, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_fe_invert_batch(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, a && out);
+  return host_unary(ctx, a, n * 40, out, n * 40, [&](void* di, void* dout) {
+    return zc_fe_invert_batch_dev(ctx, (const uint64_t*)di, (uint64_t*)dout, n);
+  });
+}
+
+int32_t zc_point_to_affine_batch_dev(zc_ctx* ctx, const uint64_t* p, uint64_t* out_xy, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, p && out_xy);
+  pt_to_affine_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(p, out_xy, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_point_to_affine_batch(zc_ctx* ctx, const uint64_t* p, uint64_t* out_xy, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, p && out_xy);
+  return host_unary(ctx, p, n * 160, out_xy, n * 80, [&](void* di, void* dout) {
+    return zc_point_to_affine_batch_dev(ctx, (const uint64_t*)di, (uint64_t*)dout, n);
+  });
+}
+
+int32_t zc_ristretto_compress_batch_dev(zc_ctx* ctx, const uint64_t* p, uint8_t* out_bytes, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, p && out_bytes);
+  ristretto_compress_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(p, out_bytes, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_ristretto_compress_batch(zc_ctx* ctx, const uint64_t* p, uint8_t* out_bytes, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, p && out_bytes);
+  return host_unary(ctx, p, n * 160, out_bytes, n * 32, [&](void* di, void* dout) {
+    return zc_ristretto_compress_batch_dev(ctx, (const uint64_t*)di, (uint8_t*)dout, n);
+  });
+}
+
+}  // extern "C"

@@ -119,6 +119,20 @@ int32_t zc_point_neg_batch_dev(zc_ctx *ctx, const uint64_t *p, uint64_t *out, si
 int32_t zc_point_scalar_mul_batch_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, uint64_t *out, size_t n, int32_t mode);
 int32_t zc_ristretto_eq_batch_dev(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint8_t *eq, size_t n);
 
+/* ---- canonicalisation: the wire-format step right after the hot path ----------------------
+ * The reference computes these with data-dependent loops (Savas-Koc inverse, Tonelli-Shanks); each returns a uniquely
+ * defined value, evaluated here with fixed exponent chains (a^(p-2); the p = 5 mod 8 square-root-ratio recipe), so the
+ * outputs are bit-identical.  out_bytes of the _dev variant must be 16-byte aligned. */
+/* replaces FieldElement::inverse field.rs:854-925 (the reference panics on 0, field.rs:864; here inverse(0) = 0) */
+int32_t zc_fe_invert_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_fe_invert_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+/* replaces AffinePoint::from(EdwardsPoint) edwards.rs:1085-1092: out_xy[i] = (X/Z, Y/Z) as uint64_t[10] */
+int32_t zc_point_to_affine_batch(zc_ctx *ctx, const uint64_t *p, uint64_t *out_xy, size_t n);
+int32_t zc_point_to_affine_batch_dev(zc_ctx *ctx, const uint64_t *p, uint64_t *out_xy, size_t n);
+/* replaces RistrettoPoint::compress ristretto.rs:398-425: out_bytes[i] = the 32-byte CompressedRistretto */
+int32_t zc_ristretto_compress_batch(zc_ctx *ctx, const uint64_t *p, uint8_t *out_bytes, size_t n);
+int32_t zc_ristretto_compress_batch_dev(zc_ctx *ctx, const uint64_t *p, uint8_t *out_bytes, size_t n);
+
 /* ---- multi-scalar multiplication  out = sum_i [s_i] P_i  (new capability; the reference has none) ---
  * Semantics = fold(Add, identity, [double_and_add(P_i, s_i)]) (edwards.rs:102-120, 465-489) as a GROUP ELEMENT: the
  * returned (X:Y:Z:T) is a valid representative, compare with affine / Ristretto equality.  Pippenger with signed

@@ -219,6 +219,58 @@ def test_ristretto_vectors_via_scalar_mul(zc, oracle, kats):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# batched canonicalisation (inverse, extended -> affine, Ristretto compress)
+# ---------------------------------------------------------------------------------------------------------
+def test_fe_invert(zc, oracle, kats):
+    """savas_koc_inverse field.rs:1531-1547 (INV_MOD_A/B/C) + random values; a * a^-1 = 1."""
+    b = zc.batch
+    for nm in "ABC":
+        assert np.array_equal(b.fe_invert(F(kats, nm))[0], F(kats, "INV_MOD_" + nm)), nm
+    a = oracle.synth_fe(SEED, 71, 0, 512)
+    a[0] = oracle.int_to_limbs(1)
+    a[1] = b.fe_neg(oracle.int_to_limbs(1))[0]           # p - 1
+    inv = b.fe_invert(a)
+    one = np.tile(oracle.int_to_limbs(1), (512, 1))
+    assert np.array_equal(b.fe_mul(a, inv), one)
+    for i in range(0, 512, 37):
+        assert np.array_equal(inv[i], oracle.fe_inverse(a[i])), i
+    assert np.array_equal(b.fe_invert(np.zeros((1, 5), np.uint64))[0], np.zeros(5, np.uint64))
+
+
+def test_point_to_affine(zc, oracle):
+    """AffinePoint::from(EdwardsPoint) edwards.rs:1085-1092, limb-exact vs the oracle (Z != 1 inputs)."""
+    P = synth_points(oracle, 72, 300)
+    got = zc.batch.point_to_affine(P)
+    want = oracle.pt_to_affine_batch(P, threads=8)
+    assert np.array_equal(got, want)
+
+
+def test_ristretto_compress(zc, oracle, kats):
+    """RistrettoPoint::compress ristretto.rs:398-425: the reference's hex vectors for [0..15]B (ristretto.rs:541-579)
+    and byte equality with the oracle on random points, their negations and torsion-shifted copies (P + P and -P)."""
+    B = C(kats, "BASEPOINT")
+    enc = kats["ristretto"]["small_multiples_hex"]
+    acc = [oracle.pt_identity()]
+    for k in range(1, 16):
+        acc.append(oracle.pt_add(acc[-1], B))
+    got = zc.batch.ristretto_compress(np.array(acc, dtype=np.uint64))
+    for k in range(16):
+        assert got[k].tobytes() == oracle.ris_compress(acc[k]), k
+        if enc is not None:
+            assert got[k].tobytes().hex() == enc[k], k
+    P = synth_points(oracle, 73, 400)
+    Q = np.concatenate([P, zc.batch.point_neg(P), zc.batch.point_double(P)])
+    got = zc.batch.ristretto_compress(Q)
+    want = oracle.ris_compress_batch(Q, threads=8)
+    assert np.array_equal(got, want)
+    # same group element, different representative (fast scalar-mul output) -> same bytes
+    s = oracle.synth_scalar(SEED, 74, 0, 64)
+    a = zc.batch.point_scalar_mul(P[:64], s, mode=0)
+    f = zc.batch.point_scalar_mul(P[:64], s, mode=1)
+    assert np.array_equal(zc.batch.ristretto_compress(a), zc.batch.ristretto_compress(f))
+
+
+# ---------------------------------------------------------------------------------------------------------
 # config 5: MSM (derived oracle: fold of double_and_add, SURVEY.md 8c)
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,c", [(1, 16), (2, 8), (33, 8), (1000, 10), (4096, 13), (4096, 16)])
