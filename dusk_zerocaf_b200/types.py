@@ -138,6 +138,11 @@ class EdwardsPoint:
         b = batch.fe_mul(np.stack([o.limbs[0:5], o.limbs[5:10]]), np.stack([self.limbs[10:15], self.limbs[10:15]]))
         return bool(np.array_equal(a, b))
 
+    def to_affine(self):
+        """AffinePoint::from(EdwardsPoint) (edwards.rs:1085-1092): (x, y) as FieldElements."""
+        xy = batch.point_to_affine(self.limbs)[0]
+        return FieldElement(xy[0:5]), FieldElement(xy[5:10])
+
     def __hash__(self): return hash(self.limbs.tobytes())
     def __repr__(self): return f"{type(self).__name__}(X={self.X}, Y={self.Y}, Z={self.Z}, T={self.T})"
 
@@ -149,5 +154,9 @@ class RistrettoPoint(EdwardsPoint):
     def __eq__(self, o):                          # ristretto.rs:166-176
         if not isinstance(o, RistrettoPoint): return False
         return bool(batch.ristretto_eq(self.limbs, o.limbs)[0])
+
+    def compress(self):
+        """RistrettoPoint::compress (ristretto.rs:398-425): the 32-byte CompressedRistretto."""
+        return batch.ristretto_compress(self.limbs)[0].tobytes()
 
     def __hash__(self): return hash(self.limbs.tobytes())

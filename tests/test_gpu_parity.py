@@ -352,3 +352,7 @@ def test_operator_surface(zc, kats, oracle):
     assert (P1 - P1) == zc.EdwardsPoint.identity()
     R1 = zc.RistrettoPoint(E(kats, "P1_EXTENDED"))
     assert R1 + R1 == R1.double() and not (R1 == R1.double())
+    assert R1.compress() == oracle.ris_compress(E(kats, "P1_EXTENDED"))
+    x, y = P1.to_affine()
+    want = oracle.pt_to_affine(E(kats, "P1_EXTENDED"))
+    assert np.array_equal(x.limbs, want[0:5]) and np.array_equal(y.limbs, want[5:10])
