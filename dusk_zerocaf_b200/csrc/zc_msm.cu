@@ -200,18 +200,73 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restr
 constexpr int SEG = 32;
 constexpr int ACC_TPB = 128;
 
-__device__ __forceinline__ PtCached ld_entry(const uint32_t* __restrict__ cached, uint32_t e) {
-  PtCached c = ld_cached(cached + 32 * (size_t)(e & 0x7fffffffu));
-  if (e >> 31) c = pt_cached_neg(c);
-  return c;
+// Operands are gathered into shared memory with cp.async (no register staging) one entry ahead of the addition that
+// uses them, and the addition reads each 32-byte coordinate from shared memory right before the multiplication that
+// consumes it: the kernel holds the accumulator and one product's temporaries in registers instead of the accumulator
+// plus two whole operands (166 -> <= 128 registers, 3 -> 4 resident CTAs per SM).
+// Stage layout: [buffer 0..1][16-byte piece 0..7][thread]; pieces 0-1 = Y+X, 2-3 = Y-X, 4-5 = Z, 6-7 = 2dT.
+constexpr int ACC_NBUF = 2;
+
+__device__ __forceinline__ void gather_entry(uint4* __restrict__ stage_buf, const uint32_t* __restrict__ cached, uint32_t e, int tx) {
+  const uint32_t* src = cached + 32 * (size_t)(e & 0x7fffffffu);
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage_buf + tx);
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(k * ACC_TPB * 16)), "l"(src + 4 * k) : "memory");
+}
+__device__ __forceinline__ Fe lds_fe(const uint4* __restrict__ p) {      // two pieces, ACC_TPB apart
+  const uint4 lo = p[0], hi = p[ACC_TPB];
+  return Fe{{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+}
+// One out-of-line copy of the multiplier: the accumulation loop body shrinks from ~35 KB of straight-line code to ~6 KB.
+// With 16 warps per SM at different points of the loop, instruction fetch was the top stall reason (no_instruction 1.3
+// per issue -> 0.07); alone the kernel is 4 % slower for the call overhead, inside the MSM (sharing SMs with the side
+// stream, 104 registers instead of 125) the whole 2^20-point MSM is 3 % faster.  A rolled-loop inline multiplier
+// (mont_mul_rolled) was slower on both counts.
+__device__ __noinline__ Fe acc_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
+
+// p + (+-q) with q staged in shared memory (q points at this thread's piece 0); add-2008-hwcd-3, a = -1
+__device__ __forceinline__ Pt pt_add_staged(const Pt& p, const uint4* __restrict__ q, bool neg) {
+  typedef ModP M;
+  Fe A = acc_mul(fe_sub<M>(p.Y, p.X), lds_fe(q + (neg ? 0 : 2) * ACC_TPB));
+  Fe B = acc_mul(fe_add<M>(p.Y, p.X), lds_fe(q + (neg ? 2 : 0) * ACC_TPB));
+  Fe t2d = lds_fe(q + 6 * ACC_TPB);
+  if (neg) t2d = fe_neg<M>(t2d);
+  Fe C = acc_mul(p.T, t2d);
+  Fe D = acc_mul(p.Z, lds_fe(q + 4 * ACC_TPB));
+  D = fe_add<M>(D, D);
+  Fe E = fe_sub<M>(B, A);
+  Fe F = fe_sub<M>(D, C);
+  Fe G = fe_add<M>(D, C);
+  Fe H = fe_add<M>(B, A);
+  Pt r;
+  r.X = acc_mul(E, F);
+  r.Y = acc_mul(G, H);
+  r.Z = acc_mul(F, G);
+  r.T = acc_mul(E, H);
+  return r;
+}
+// the point a staged operand stands for, as (2X, 2Y, 2Z, 2T)
+__device__ __forceinline__ Pt staged_to_pt(const uint4* __restrict__ q, bool neg) {
+  typedef ModP M;
+  Fe ypx = lds_fe(q + (neg ? 2 : 0) * ACC_TPB), ymx = lds_fe(q + (neg ? 0 : 2) * ACC_TPB);
+  Fe z = lds_fe(q + 4 * ACC_TPB), t2d = lds_fe(q + 6 * ACC_TPB);
+  if (neg) t2d = fe_neg<M>(t2d);
+  Pt r;
+  r.X = fe_sub<M>(ypx, ymx);
+  r.Y = fe_add<M>(ypx, ymx);
+  r.Z = fe_add<M>(z, z);
+  r.T = acc_mul(t2d, DINV_MONT());
+  return r;
 }
 
-__global__ void __launch_bounds__(ACC_TPB) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
-                                                            const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                            size_t n_pad, int nseg, int nwl, int nb,
-                                                            uint32_t* __restrict__ buckets, uint32_t* __restrict__ partH,
-                                                            uint32_t* __restrict__ partT) {
+__global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
+                                                               const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
+                                                               size_t n_pad, int nseg, int nwl, int nb,
+                                                               uint32_t* __restrict__ buckets, uint32_t* __restrict__ partH,
+                                                               uint32_t* __restrict__ partT) {
   __shared__ uint32_t idx_s[SEG * ACC_TPB];
+  __shared__ __align__(16) uint4 stage[ACC_NBUF][8 * ACC_TPB];
   const int tx = threadIdx.x;
   size_t g = (size_t)blockIdx.x * ACC_TPB + tx;
   if (g >= (size_t)nwl * nseg) return;
@@ -232,6 +287,9 @@ __global__ void __launch_bounds__(ACC_TPB) msm_accum_kernel(const uint32_t* __re
       idx_s[(4 * j + 2) * ACC_TPB + tx] = v.z; idx_s[(4 * j + 3) * ACC_TPB + tx] = v.w;
     }
   }
+  uint32_t e_cur = idx_s[tx];
+  gather_entry(stage[0], cached, e_cur, tx);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   // bucket of the first entry: last b with offs[b] <= start  (upper_bound - 1)
   uint32_t lo = 0, hi = (uint32_t)nb;
   while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (woffs[mid] <= start) lo = mid + 1; else hi = mid; }
@@ -242,25 +300,33 @@ __global__ void __launch_bounds__(ACC_TPB) msm_accum_kernel(const uint32_t* __re
   uint32_t* pH = partH + 32 * g;
   uint32_t* pT = partT + 32 * g;
 
-  PtCached cur = ld_entry(cached, idx_s[tx]);
-  Pt acc = cached_to_pt(cur);
-  if (start + 1 < end) cur = ld_entry(cached, idx_s[ACC_TPB + tx]);
+  Pt acc;
 #pragma unroll 1
-  for (uint32_t k = start + 1; k < end; k++) {
-    PtCached nxt = cur;
-    if (k + 1 < end) nxt = ld_entry(cached, idx_s[(k + 1 - start) * ACC_TPB + tx]);   // prefetch: independent of acc
-    if (k == bend) {
+  for (uint32_t k = start; k < end; k++) {
+    const int buf = (k - start) & 1;
+    uint32_t e_nxt = 0;
+    if (k + 1 < end) {                       // gather the next operand under this addition
+      e_nxt = idx_s[(k + 1 - start) * ACC_TPB + tx];
+      gather_entry(stage[buf ^ 1], cached, e_nxt, tx);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");     // everything but the newest group: entry k has landed
+    const uint4* q = stage[buf] + tx;
+    const bool neg = (e_cur >> 31) != 0;
+    if (k == start) {
+      acc = staged_to_pt(q, neg);
+    } else if (k == bend) {
       // flush the finished run
       const bool complete = (run_start == bbeg);
       st_pt(complete ? bk + 32 * (size_t)b : pH, acc);   // incomplete here <=> the run began before this segment (H slot)
       do { b++; } while (whist[b] == 0);
       bbeg = k; bend = k + whist[b];
       run_start = k;
-      acc = cached_to_pt(cur);
+      acc = staged_to_pt(q, neg);
     } else {
-      acc = pt_add_cached(acc, cur);
+      acc = pt_add_staged(acc, q, neg);
     }
-    cur = nxt;
+    e_cur = e_nxt;
   }
   {
     const bool complete = (run_start == bbeg) && (end == bend);
