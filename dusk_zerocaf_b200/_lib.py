@@ -79,6 +79,8 @@ def lib():
         getattr(L, f"zc_msm{suf}").argtypes = [vp, vp, vp, sz, i32, vp]
         for nm in ("zc_fe_invert_batch", "zc_point_to_affine_batch", "zc_ristretto_compress_batch"):
             getattr(L, nm + suf).argtypes = [vp, vp, vp, sz]
+        getattr(L, "zc_point_is_valid_batch" + suf).argtypes = [vp, vp, vp, sz]
+        getattr(L, "zc_ristretto_decompress_batch" + suf).argtypes = [vp, vp, vp, vp, sz]
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
     L.zc_msm_partial_dev.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
     L.zc_point_fold_dev.argtypes = [vp, vp, sz, vp]

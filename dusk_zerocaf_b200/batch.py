@@ -100,6 +100,25 @@ def ristretto_compress(p, ctx=None):
     return out
 
 
+def ristretto_decompress(encodings, ctx=None):
+    """CompressedRistretto::decompress (ristretto.rs:96-154): ((n, 20) points, (n,) ok flags); ok == 0 <=> None."""
+    ctx = ctx or default_context()
+    e = np.ascontiguousarray(encodings, dtype=np.uint8).reshape(-1, 32)
+    out = np.empty((e.shape[0], 20), dtype=np.uint64)
+    ok = np.empty(e.shape[0], dtype=np.uint8)
+    ctx.call("zc_ristretto_decompress_batch", e, out, ok, e.shape[0])
+    return out, ok
+
+
+def point_is_valid(p, ctx=None):
+    """ValidityCheck for EdwardsPoint (edwards.rs:393-400): the curve equation in projective coordinates."""
+    ctx = ctx or default_context()
+    p = _arr(p, 20)
+    ok = np.empty(p.shape[0], dtype=np.uint8)
+    ctx.call("zc_point_is_valid_batch", p, ok, p.shape[0])
+    return ok
+
+
 def msm(points, scalars, window_bits=16, ctx=None):
     """sum_i [s_i] P_i as an EdwardsPoint (20 limbs); a group element, compare canonically."""
     ctx = ctx or default_context()

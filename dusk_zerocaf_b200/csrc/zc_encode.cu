@@ -4,6 +4,9 @@
 //   zc_point_to_affine_batch    AffinePoint::from(EdwardsPoint)     /root/reference/src/edwards.rs:1085-1092
 //   zc_ristretto_compress_batch RistrettoPoint::compress            /root/reference/src/ristretto.rs:398-425
 //                               (inv_sqrt / sqrt_ratio_i field.rs:443-503, is_positive :552-557, to_bytes :591-631)
+// and the step right before it (8f rank 2):
+//   zc_ristretto_decompress_batch CompressedRistretto::decompress   /root/reference/src/ristretto.rs:96-154
+//   zc_point_is_valid_batch       ValidityCheck for EdwardsPoint    /root/reference/src/edwards.rs:393-400, 733-748
 //
 // The reference computes these with data-dependent loops (Savas-Koc almost-Montgomery inverse, Tonelli-Shanks); every
 // one of them returns a uniquely defined VALUE (the inverse; the non-negative root), so the device code evaluates the
@@ -63,7 +66,7 @@ __device__ __forceinline__ bool fe_is_positive(const Fe& x) {
 __device__ __forceinline__ bool mont_is_positive(const Fe& xm) { return fe_is_positive(from_mont<ModP>(xm)); }
 
 // (was_square, +sqrt(1/v)) or (0, +sqrt(i/v)); v = 0 -> (0, 0).  Montgomery form in and out.     field.rs:443-503
-__device__ __forceinline__ Fe mont_inv_sqrt(const Fe& v) {
+__device__ __forceinline__ Fe mont_inv_sqrt(const Fe& v, bool& was_square) {
   typedef ModP M;
   const Fe one = Consts<M>::R1(), i = SQRT_M1_MONT();
   Fe v2 = mul_ni(v, v);
@@ -72,11 +75,12 @@ __device__ __forceinline__ Fe mont_inv_sqrt(const Fe& v) {
   Fe r = mul_ni(v3, fe_pow_const(v7, E_SQRT, 250));
   Fe check = mul_ni(v, mul_ni(r, r));
   // check is one of 1, -1 (r <- i r), -i (r <- i r, non-square), i (non-square); 0 when v = 0 (r = 0 already)
-  const bool flip = fe_eq(check, MINUS_ONE_MONT()) || fe_eq(check, fe_neg<M>(i));
+  const bool minus_one = fe_eq(check, MINUS_ONE_MONT());
+  was_square = minus_one || fe_eq(check, one);
+  const bool flip = minus_one || fe_eq(check, fe_neg<M>(i));
   Fe ri = mul_ni(r, i);
   if (flip) r = ri;
   if (!mont_is_positive(r)) r = fe_neg<M>(r);
-  (void)one;
   return r;
 }
 
@@ -106,7 +110,8 @@ __global__ void __launch_bounds__(TPB) ristretto_compress_kernel(const uint64_t*
   const Fe i = SQRT_M1_MONT();
   Fe u1 = mul_ni(fe_add<M>(P.Z, P.Y), fe_sub<M>(P.Z, P.Y));
   Fe u2 = mul_ni(P.X, P.Y);
-  Fe I = mont_inv_sqrt(mul_ni(u1, mul_ni(u2, u2)));
+  bool sq;
+  Fe I = mont_inv_sqrt(mul_ni(u1, mul_ni(u2, u2)), sq);
   Fe D1 = mul_ni(u1, I);
   Fe D2 = mul_ni(u2, I);
   Fe Zinv = mul_ni(mul_ni(D1, D2), P.T);
@@ -123,6 +128,60 @@ __global__ void __launch_bounds__(TPB) ristretto_compress_kernel(const uint64_t*
   uint4* o = reinterpret_cast<uint4*>(out + 32 * idx);
   o[0] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
   o[1] = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+}
+
+// Ristretto decoding: ok[i] = 1 and out[i] = (x, y, 1, x y), or ok[i] = 0 and out[i] = 0            ristretto.rs:96-154
+// from_bytes keeps all 256 bits (field.rs:563-587), so the reference's re-encoding check always passes and step 1 reduces
+// to is_positive: the encoded integer must be <= (p-1)/2.
+__global__ void __launch_bounds__(TPB) ristretto_decompress_kernel(const uint8_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                                   uint8_t* __restrict__ ok, size_t n) {
+  typedef ModP M;
+  size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (idx >= n) return;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(in + 32 * idx);
+  Fe sn{{w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]}};
+  bool good = fe_is_positive(sn);
+  if (!good) sn = Fe{{0, 0, 0, 0, 0, 0, 0, 0}};            // keep the arithmetic below on canonical input
+  const Fe one = Consts<M>::R1();
+  Fe s = to_mont<M>(sn);
+  Fe ss = mul_ni(s, s);
+  Fe u1 = fe_sub<M>(one, ss);                              // 1 + a s^2, a = -1
+  Fe u2 = fe_add<M>(one, ss);
+  Fe u2_sq = mul_ni(u2, u2);
+  Fe v = fe_sub<M>(fe_neg<M>(mul_ni(D_MONT(), mul_ni(u1, u1))), u2_sq);
+  bool sq;
+  Fe I = mont_inv_sqrt(mul_ni(v, u2_sq), sq);
+  good = good && sq;
+  Fe Dx = mul_ni(I, u2);
+  Fe Dy = mul_ni(mul_ni(I, Dx), v);
+  Fe x = mul_ni(fe_add<M>(s, s), Dx);
+  if (!mont_is_positive(x)) x = fe_neg<M>(x);
+  Fe y = mul_ni(u1, Dy);
+  Fe t = mul_ni(x, y);
+  good = good && mont_is_positive(t) && !fe_is_zero(y);
+  uint64_t* o = out + 20 * idx;
+  if (good) {
+    fe_store52(o, from_mont<M>(x));
+    fe_store52(o + 5, from_mont<M>(y));
+    o[10] = 1; o[11] = 0; o[12] = 0; o[13] = 0; o[14] = 0;
+    fe_store52(o + 15, from_mont<M>(t));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 20; k++) o[k] = 0;
+  }
+  ok[idx] = good ? 1 : 0;
+}
+
+// (a X^2 + Y^2) Z^2 == Z^4 + d X^2 Y^2                                                        edwards.rs:733-748
+__global__ void __launch_bounds__(TPB) pt_is_valid_kernel(const uint64_t* __restrict__ p, uint8_t* __restrict__ ok, size_t n) {
+  typedef ModP M;
+  size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (idx >= n) return;
+  Fe X = to_mont<M>(fe_load52(p + 20 * idx)), Y = to_mont<M>(fe_load52(p + 20 * idx + 5)), Z = to_mont<M>(fe_load52(p + 20 * idx + 10));
+  Fe xx = mul_ni(X, X), yy = mul_ni(Y, Y), zz = mul_ni(Z, Z);
+  Fe left = mul_ni(fe_sub<M>(yy, xx), zz);
+  Fe right = fe_add<M>(mul_ni(zz, zz), mul_ni(mul_ni(D_MONT(), xx), yy));
+  ok[idx] = fe_eq(left, right) ? 1 : 0;
 }
 
 inline unsigned grid_for(size_t n) { return (unsigned)((n + TPB - 1) / TPB); }
@@ -194,6 +253,43 @@ int32_t zc_ristretto_compress_batch(zc_ctx* ctx, const uint64_t* p, uint8_t* out
   ZC_ENC_PROLOGUE(ctx, n, p && out_bytes);
   return host_unary(ctx, p, n * 160, out_bytes, n * 32, [&](void* di, void* dout) {
     return zc_ristretto_compress_batch_dev(ctx, (const uint64_t*)di, (uint8_t*)dout, n);
+  });
+}
+
+int32_t zc_ristretto_decompress_batch_dev(zc_ctx* ctx, const uint8_t* in_bytes, uint64_t* out_points, uint8_t* ok, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, in_bytes && out_points && ok);
+  if ((uintptr_t)in_bytes & 3u) return zc_fail(ctx, ZC_ERR_SIZE, "in_bytes must be 4-byte aligned");
+  ristretto_decompress_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(in_bytes, out_points, ok, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_ristretto_decompress_batch(zc_ctx* ctx, const uint8_t* in_bytes, uint64_t* out_points, uint8_t* ok, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, in_bytes && out_points && ok);
+  void *din = nullptr, *dout = nullptr, *dok = nullptr;
+  int32_t rc;
+  if ((rc = zc_scratch(ctx, 0, n * 32, &din))) return rc;
+  if ((rc = zc_scratch(ctx, 2, n * 160, &dout))) return rc;
+  if ((rc = zc_scratch(ctx, 1, n, &dok))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(din, in_bytes, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = zc_ristretto_decompress_batch_dev(ctx, (const uint8_t*)din, (uint64_t*)dout, (uint8_t*)dok, n))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(out_points, dout, n * 160, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZC_OK;
+}
+
+int32_t zc_point_is_valid_batch_dev(zc_ctx* ctx, const uint64_t* p, uint8_t* ok, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, p && ok);
+  pt_is_valid_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(p, ok, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_point_is_valid_batch(zc_ctx* ctx, const uint64_t* p, uint8_t* ok, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, p && ok);
+  return host_unary(ctx, p, n * 160, ok, n, [&](void* di, void* dout) {
+    return zc_point_is_valid_batch_dev(ctx, (const uint64_t*)di, (uint8_t*)dout, n);
   });
 }
 

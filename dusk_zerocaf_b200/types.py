@@ -159,4 +159,10 @@ class RistrettoPoint(EdwardsPoint):
         """RistrettoPoint::compress (ristretto.rs:398-425): the 32-byte CompressedRistretto."""
         return batch.ristretto_compress(self.limbs)[0].tobytes()
 
+    @classmethod
+    def decompress(cls, encoding):
+        """CompressedRistretto::decompress (ristretto.rs:96-154): a RistrettoPoint, or None."""
+        pts, ok = batch.ristretto_decompress(np.frombuffer(bytes(encoding), dtype=np.uint8))
+        return cls(pts[0]) if ok[0] else None
+
     def __hash__(self): return hash(self.limbs.tobytes())

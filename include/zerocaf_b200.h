@@ -132,6 +132,14 @@ int32_t zc_point_to_affine_batch_dev(zc_ctx *ctx, const uint64_t *p, uint64_t *o
 /* replaces RistrettoPoint::compress ristretto.rs:398-425: out_bytes[i] = the 32-byte CompressedRistretto */
 int32_t zc_ristretto_compress_batch(zc_ctx *ctx, const uint64_t *p, uint8_t *out_bytes, size_t n);
 int32_t zc_ristretto_compress_batch_dev(zc_ctx *ctx, const uint64_t *p, uint8_t *out_bytes, size_t n);
+/* replaces CompressedRistretto::decompress ristretto.rs:96-154 (the step right before the path):
+ * ok[i] = 1 and out_points[i] = (x, y, 1, xy) where the reference returns Some(point); ok[i] = 0 and a zeroed point where
+ * it returns None (negative or non-canonical s, non-square, negative t, y = 0).  in_bytes must be 4-byte aligned (_dev). */
+int32_t zc_ristretto_decompress_batch(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out_points, uint8_t *ok, size_t n);
+int32_t zc_ristretto_decompress_batch_dev(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out_points, uint8_t *ok, size_t n);
+/* replaces ValidityCheck for EdwardsPoint edwards.rs:393-400, 733-748: ok[i] = 1 iff (aX^2 + Y^2) Z^2 == Z^4 + d X^2 Y^2 */
+int32_t zc_point_is_valid_batch(zc_ctx *ctx, const uint64_t *p, uint8_t *ok, size_t n);
+int32_t zc_point_is_valid_batch_dev(zc_ctx *ctx, const uint64_t *p, uint8_t *ok, size_t n);
 
 /* ---- multi-scalar multiplication  out = sum_i [s_i] P_i  (new capability; the reference has none) ---
  * Semantics = fold(Add, identity, [double_and_add(P_i, s_i)]) (edwards.rs:102-120, 465-489) as a GROUP ELEMENT: the

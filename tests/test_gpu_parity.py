@@ -270,6 +270,46 @@ def test_ristretto_compress(zc, oracle, kats):
     assert np.array_equal(zc.batch.ristretto_compress(a), zc.batch.ristretto_compress(f))
 
 
+def test_ristretto_decompress_and_validity(zc, oracle, kats):
+    """CompressedRistretto::decompress ristretto.rs:96-154 and ValidityCheck edwards.rs:393-400, limb-exact vs the oracle:
+    the [0..15]B vectors (basepoint_compr_decompr :533, decompress_id :582), round trips of random points, and
+    encodings the reference rejects (negative s, s >= p, random bytes: non-squares / negative t)."""
+    b = zc.batch
+    enc = kats["ristretto"]["small_multiples_hex"]
+    rng = np.random.default_rng(20261017)
+    P = synth_points(oracle, 75, 300)
+    good = b.ristretto_compress(P)
+    p = 2**252 + 27742317777372353535851937790883648493
+    bad = []
+    for k in range(40):
+        v = int.from_bytes(good[k].tobytes(), "little")
+        bad.append(np.frombuffer((p - v).to_bytes(32, "little"), dtype=np.uint8) if v else good[k])   # negative s
+    bad.append(np.frombuffer((p + 5).to_bytes(32, "little"), dtype=np.uint8))                         # s >= p
+    bad.append(np.full(32, 0xff, dtype=np.uint8))
+    rnd = rng.integers(0, 256, size=(300, 32), dtype=np.uint8)
+    rnd[:, 31] &= 0x0f                                                                               # many below (p-1)/2
+    vec = [np.frombuffer(bytes.fromhex(h), dtype=np.uint8) for h in enc] if enc is not None else []
+    allenc = np.concatenate([np.array(vec, dtype=np.uint8).reshape(-1, 32), good, np.array(bad, dtype=np.uint8), rnd])
+    pts, ok = b.ristretto_decompress(allenc)
+    n_some = 0
+    for i in range(allenc.shape[0]):
+        want = oracle.ris_decompress(allenc[i])
+        assert (want is not None) == bool(ok[i]), i
+        if want is not None:
+            n_some += 1
+            assert np.array_equal(pts[i], want), i
+    assert n_some >= len(vec) + 300 and n_some < allenc.shape[0]          # both branches exercised
+    # decode(encode(P)) is P up to 4-torsion: Ristretto-equal, and re-encodes to the same bytes
+    dec = pts[len(vec):len(vec) + 300]
+    assert b.ristretto_eq(dec, P).all()
+    assert np.array_equal(b.ristretto_compress(dec), good)
+    # validity: decoded points and extended-coordinate points satisfy the curve equation, a perturbed one does not
+    assert b.point_is_valid(dec).all() and b.point_is_valid(P).all()
+    Q = P[:8].copy(); Q[:, 0] ^= np.uint64(1)
+    got = b.point_is_valid(Q)
+    assert [int(x) for x in got] == [oracle.pt_is_valid(q) for q in Q] and not got.any()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # config 5: MSM (derived oracle: fold of double_and_add, SURVEY.md 8c)
 # ---------------------------------------------------------------------------------------------------------
