@@ -80,6 +80,7 @@ def lib():
         for nm in ("zc_fe_invert_batch", "zc_point_to_affine_batch", "zc_ristretto_compress_batch"):
             getattr(L, nm + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_point_is_valid_batch" + suf).argtypes = [vp, vp, vp, sz]
+        getattr(L, "zc_basepoint_mul_batch" + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_ristretto_decompress_batch" + suf).argtypes = [vp, vp, vp, vp, sz]
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
     L.zc_msm_partial_dev.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]

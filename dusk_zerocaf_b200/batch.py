@@ -69,6 +69,15 @@ def point_scalar_mul(points, scalars, mode=0, ctx=None):
     return out
 
 
+def basepoint_mul(scalars, ctx=None):
+    """[s_i] B for the basepoint (constants.rs:188-211) through the fixed-base table; compare canonically."""
+    ctx = ctx or default_context()
+    s = _arr(scalars, 5)
+    out = np.empty((s.shape[0], 20), dtype=np.uint64)
+    ctx.call("zc_basepoint_mul_batch", s, out, s.shape[0])
+    return out
+
+
 def ristretto_eq(p, q, ctx=None):
     ctx = ctx or default_context()
     p, q = _arr(p, 20), _arr(q, 20)

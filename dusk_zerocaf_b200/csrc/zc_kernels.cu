@@ -342,6 +342,7 @@ int32_t zc_ctx_destroy(zc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 6; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->msm_ws) cudaFree(ctx->msm_ws);
+  if (ctx->basepoint_table) cudaFree(ctx->basepoint_table);
   if (ctx->gather_buf) cudaFree(ctx->gather_buf);
   if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); for (int i = 0; i < 2 * ZC_PIPE_MAX_CHUNKS; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]); }
   if (ctx->msm_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec);

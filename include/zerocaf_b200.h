@@ -119,6 +119,13 @@ int32_t zc_point_neg_batch_dev(zc_ctx *ctx, const uint64_t *p, uint64_t *out, si
 int32_t zc_point_scalar_mul_batch_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, uint64_t *out, size_t n, int32_t mode);
 int32_t zc_ristretto_eq_batch_dev(zc_ctx *ctx, const uint64_t *p, const uint64_t *q, uint8_t *eq, size_t n);
 
+/* Fixed-base scalar multiplication out[i] = [s_i] B for the basepoint (constants.rs:188-211): replaces
+ * `&BASEPOINT * &scalar` (edwards.rs:547-577) and is the working equivalent of the reference's untested fixed-base
+ * window_naf_mul (edwards.rs:155-171).  Signed radix-16 digits over a 48 KiB table of affine cached multiples built on the
+ * device on first use; same group element as double_and_add, other representative (compare canonically). */
+int32_t zc_basepoint_mul_batch(zc_ctx *ctx, const uint64_t *scalars, uint64_t *out, size_t n);
+int32_t zc_basepoint_mul_batch_dev(zc_ctx *ctx, const uint64_t *scalars, uint64_t *out, size_t n);
+
 /* ---- canonicalisation: the wire-format step right after the hot path ----------------------
  * The reference computes these with data-dependent loops (Savas-Koc inverse, Tonelli-Shanks); each returns a uniquely
  * defined value, evaluated here with fixed exponent chains (a^(p-2); the p = 5 mod 8 square-root-ratio recipe), so the

@@ -203,6 +203,30 @@ def test_scalar_mul_fast(zc, oracle):
     assert oracle.ris_compress(got[17]) == oracle.ris_compress(want[17])
 
 
+def test_basepoint_mul_fixed_base(zc, oracle, kats):
+    """[s]B through the fixed-base table == double_and_add(B, s) as a group element (edwards.rs:547-577): the reference's
+    [0..15]B encodings, edge scalars ([L-1]B + B = O, unique_basepoint_test edwards.rs:1593-1600) and random scalars."""
+    B = C(kats, "BASEPOINT")
+    enc = kats["ristretto"]["small_multiples_hex"]
+    L = 2**249 + 14490550575682688738086195780655237219
+    edge = [0, 1, 2, 7, 8, 9, 15, 16, L - 1, L - 2, 2**249 - 1, 2**249, 2**248, 0x8888888888888888, 0x7777777777777777 << 180]
+    s = np.concatenate([np.array([oracle.int_to_limbs(k) for k in list(range(16)) + edge], dtype=np.uint64),
+                        oracle.synth_scalar(SEED, 76, 0, 400)])
+    got = zc.batch.basepoint_mul(s)
+    want = oracle.pt_scalar_mul_batch(np.tile(B, (s.shape[0], 1)), s, threads=8)
+    for i in range(s.shape[0]):
+        assert oracle.pt_is_valid(got[i]), i
+        assert oracle.pt_eq(got[i], want[i]), i
+    cg = zc.batch.ristretto_compress(got)
+    if enc is not None:
+        for k in range(16):
+            assert cg[k].tobytes().hex() == enc[k], k
+    assert oracle.pt_eq(oracle.pt_add(got[16 + 8], B), oracle.pt_identity())          # [L-1]B + B
+    # agrees with the variable-base kernels on a larger batch
+    s2 = oracle.synth_scalar(SEED, 77, 0, 5000)
+    assert zc.batch.ristretto_eq(zc.batch.basepoint_mul(s2), zc.batch.point_scalar_mul(np.tile(B, (5000, 1)), s2, mode=1)).all()
+
+
 def test_ristretto_vectors_via_scalar_mul(zc, oracle, kats):
     """valid_encoding_test_vectors ristretto.rs:541-579: compress([k]B), k = 0..15."""
     B = C(kats, "BASEPOINT")
