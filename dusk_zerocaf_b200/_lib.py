@@ -81,6 +81,8 @@ def lib():
             getattr(L, nm + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_point_is_valid_batch" + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_basepoint_mul_batch" + suf).argtypes = [vp, vp, vp, sz]
+        getattr(L, "zc_ristretto_elligator_batch" + suf).argtypes = [vp, vp, vp, sz]
+        getattr(L, "zc_ristretto_from_uniform_bytes_batch" + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_ristretto_decompress_batch" + suf).argtypes = [vp, vp, vp, vp, sz]
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
     L.zc_msm_partial_dev.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]

@@ -119,6 +119,24 @@ def ristretto_decompress(encodings, ctx=None):
     return out, ok
 
 
+def ristretto_elligator(r0, ctx=None):
+    """RistrettoPoint::elligator_ristretto_flavor (ristretto.rs:430-471), limb-exact: (n, 20)."""
+    ctx = ctx or default_context()
+    r0 = _arr(r0, 5)
+    out = np.empty((r0.shape[0], 20), dtype=np.uint64)
+    ctx.call("zc_ristretto_elligator_batch", r0, out, r0.shape[0])
+    return out
+
+
+def ristretto_from_uniform_bytes(data, ctx=None):
+    """RistrettoPoint::from_uniform_bytes (ristretto.rs:493-507): (n, 64) uint8 -> (n, 20), limb-exact."""
+    ctx = ctx or default_context()
+    d = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 64)
+    out = np.empty((d.shape[0], 20), dtype=np.uint64)
+    ctx.call("zc_ristretto_from_uniform_bytes_batch", d, out, d.shape[0])
+    return out
+
+
 def point_is_valid(p, ctx=None):
     """ValidityCheck for EdwardsPoint (edwards.rs:393-400): the curve equation in projective coordinates."""
     ctx = ctx or default_context()

@@ -7,6 +7,9 @@
 // and the step right before it (8f rank 2):
 //   zc_ristretto_decompress_batch CompressedRistretto::decompress   /root/reference/src/ristretto.rs:96-154
 //   zc_point_is_valid_batch       ValidityCheck for EdwardsPoint    /root/reference/src/edwards.rs:393-400, 733-748
+// and hash-to-group (8f rank 3):
+//   zc_ristretto_elligator_batch          elligator_ristretto_flavor /root/reference/src/ristretto.rs:430-471
+//   zc_ristretto_from_uniform_bytes_batch from_uniform_bytes         /root/reference/src/ristretto.rs:493-507
 //
 // The reference computes these with data-dependent loops (Savas-Koc almost-Montgomery inverse, Tonelli-Shanks); every
 // one of them returns a uniquely defined VALUE (the inverse; the non-negative root), so the device code evaluates the
@@ -184,6 +187,72 @@ __global__ void __launch_bounds__(TPB) pt_is_valid_kernel(const uint64_t* __rest
   ok[idx] = fe_eq(left, right) ? 1 : 0;
 }
 
+// ---- hash to group -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fe ONE_MINUS_D_SQ_MONT()    { return Fe{{0xdf568a00u, 0x939bafb4u, 0xcb683c61u, 0xcf54cbd6u, 0xf592c91cu, 0xec300527u, 0x6551a020u, 0x08f2ce8eu}}; }
+__device__ __forceinline__ Fe D_MINUS_ONE_SQ_MONT()    { return Fe{{0x46acfacfu, 0xd6c8ed3du, 0x910abc15u, 0xa96623f1u, 0x2515d67au, 0x410f7878u, 0x702e8474u, 0x0f7142b0u}}; }
+__device__ __forceinline__ Fe SQRT_AD_MINUS_ONE_MONT() { return Fe{{0x9e882cc7u, 0xdf3921e3u, 0x98d6d78eu, 0xbba9f682u, 0xa71a2909u, 0xe38d903eu, 0x70c5212du, 0x030de965u}}; }   // constants.rs:132-138
+
+// (was_square, +sqrt(u/v)) or (0, +sqrt(i u/v)); u = 0 -> (1, 0); v = 0 != u -> (0, 0).          field.rs:461-503
+__device__ __forceinline__ Fe mont_sqrt_ratio_i(const Fe& u, const Fe& v, bool& was_square) {
+  typedef ModP M;
+  const Fe i = SQRT_M1_MONT();
+  Fe v2 = mul_ni(v, v);
+  Fe v3 = mul_ni(v2, v);
+  Fe v7 = mul_ni(mul_ni(v3, v3), v);
+  Fe r = mul_ni(mul_ni(u, v3), fe_pow_const(mul_ni(u, v7), E_SQRT, 250));
+  Fe check = mul_ni(v, mul_ni(r, r));
+  const Fe neg_u = fe_neg<M>(u);
+  const Fe neg_ui = mul_ni(neg_u, i);
+  const bool correct = fe_eq(check, u), flipped = fe_eq(check, neg_u), flipped_i = fe_eq(check, neg_ui);
+  Fe ri = mul_ni(r, i);
+  if (flipped || flipped_i) r = ri;
+  if (!mont_is_positive(r)) r = fe_neg<M>(r);
+  was_square = correct || flipped;
+  return r;
+}
+
+// Ristretto-flavoured Elligator 2 on a Montgomery-form r0; the returned (X:Y:Z:T) are the reference's own products
+__device__ __forceinline__ Pt elligator_mont(const Fe& r0) {
+  typedef ModP M;
+  const Fe one = Consts<M>::R1(), d = D_MONT();
+  Fe c = MINUS_ONE_MONT();
+  Fe r = mul_ni(SQRT_M1_MONT(), mul_ni(r0, r0));
+  Fe Ns = mul_ni(fe_add<M>(r, one), ONE_MINUS_D_SQ_MONT());
+  Fe D = mul_ni(fe_sub<M>(c, mul_ni(d, r)), fe_add<M>(r, d));
+  bool sq;
+  Fe s = mont_sqrt_ratio_i(Ns, D, sq);
+  Fe s_prim = mul_ni(s, r0);
+  if (mont_is_positive(s_prim)) s_prim = fe_neg<M>(s_prim);       // s' = -|s r0|
+  if (!sq) { s = s_prim; c = r; }
+  Fe Nt = fe_sub<M>(mul_ni(mul_ni(c, fe_sub<M>(r, one)), D_MINUS_ONE_SQ_MONT()), D);
+  Fe ss = mul_ni(s, s);
+  Fe W0 = mul_ni(fe_add<M>(s, s), D);
+  Fe W1 = mul_ni(Nt, SQRT_AD_MINUS_ONE_MONT());
+  Fe W2 = fe_sub<M>(one, ss);
+  Fe W3 = fe_add<M>(one, ss);
+  return Pt{mul_ni(W0, W3), mul_ni(W2, W1), mul_ni(W1, W3), mul_ni(W0, W2)};
+}
+
+// any 256-bit integer -> Montgomery form of its residue (x R^2 < R m, so one product reduces it)
+__device__ __forceinline__ Fe bytes_to_mont(const uint8_t* __restrict__ b) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(b);
+  return to_mont<ModP>(Fe{{w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]}});
+}
+
+__global__ void __launch_bounds__(TPB) ristretto_elligator_kernel(const uint64_t* __restrict__ r0, uint64_t* __restrict__ out, size_t n) {
+  size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (idx >= n) return;
+  pt_store52(out + 20 * idx, pt_from_mont(elligator_mont(to_mont<ModP>(fe_load52(r0 + 5 * idx)))));
+}
+
+__global__ void __launch_bounds__(TPB) ristretto_from_uniform_kernel(const uint8_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
+  size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (idx >= n) return;
+  Pt R1 = elligator_mont(bytes_to_mont(in + 64 * idx));
+  Pt R2 = elligator_mont(bytes_to_mont(in + 64 * idx + 32));
+  pt_store52(out + 20 * idx, pt_from_mont(pt_add_ref(R1, R2)));      // R_1 + R_2 with the reference Add
+}
+
 inline unsigned grid_for(size_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 constexpr size_t MAX_N = (size_t)1 << 31;
 
@@ -290,6 +359,35 @@ int32_t zc_point_is_valid_batch(zc_ctx* ctx, const uint64_t* p, uint8_t* ok, siz
   ZC_ENC_PROLOGUE(ctx, n, p && ok);
   return host_unary(ctx, p, n * 160, ok, n, [&](void* di, void* dout) {
     return zc_point_is_valid_batch_dev(ctx, (const uint64_t*)di, (uint8_t*)dout, n);
+  });
+}
+
+int32_t zc_ristretto_elligator_batch_dev(zc_ctx* ctx, const uint64_t* r0, uint64_t* out_points, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, r0 && out_points);
+  ristretto_elligator_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(r0, out_points, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_ristretto_elligator_batch(zc_ctx* ctx, const uint64_t* r0, uint64_t* out_points, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, r0 && out_points);
+  return host_unary(ctx, r0, n * 40, out_points, n * 160, [&](void* di, void* dout) {
+    return zc_ristretto_elligator_batch_dev(ctx, (const uint64_t*)di, (uint64_t*)dout, n);
+  });
+}
+
+int32_t zc_ristretto_from_uniform_bytes_batch_dev(zc_ctx* ctx, const uint8_t* in_bytes, uint64_t* out_points, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, in_bytes && out_points);
+  if ((uintptr_t)in_bytes & 3u) return zc_fail(ctx, ZC_ERR_SIZE, "in_bytes must be 4-byte aligned");
+  ristretto_from_uniform_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(in_bytes, out_points, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_ristretto_from_uniform_bytes_batch(zc_ctx* ctx, const uint8_t* in_bytes, uint64_t* out_points, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, in_bytes && out_points);
+  return host_unary(ctx, in_bytes, n * 64, out_points, n * 160, [&](void* di, void* dout) {
+    return zc_ristretto_from_uniform_bytes_batch_dev(ctx, (const uint8_t*)di, (uint64_t*)dout, n);
   });
 }
 

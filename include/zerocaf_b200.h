@@ -144,6 +144,13 @@ int32_t zc_ristretto_compress_batch_dev(zc_ctx *ctx, const uint64_t *p, uint8_t 
  * it returns None (negative or non-canonical s, non-square, negative t, y = 0).  in_bytes must be 4-byte aligned (_dev). */
 int32_t zc_ristretto_decompress_batch(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out_points, uint8_t *ok, size_t n);
 int32_t zc_ristretto_decompress_batch_dev(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out_points, uint8_t *ok, size_t n);
+/* Hash to group, limb-exact: the returned (X:Y:Z:T) are the reference's own products.
+ * replaces RistrettoPoint::elligator_ristretto_flavor ristretto.rs:430-471 (r0 as [u64;5] limbs, value < 2^256) */
+int32_t zc_ristretto_elligator_batch(zc_ctx *ctx, const uint64_t *r0, uint64_t *out_points, size_t n);
+int32_t zc_ristretto_elligator_batch_dev(zc_ctx *ctx, const uint64_t *r0, uint64_t *out_points, size_t n);
+/* replaces RistrettoPoint::from_uniform_bytes ristretto.rs:493-507: 64 bytes per point, Elligator on each half, R_1 + R_2 */
+int32_t zc_ristretto_from_uniform_bytes_batch(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out_points, size_t n);
+int32_t zc_ristretto_from_uniform_bytes_batch_dev(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out_points, size_t n);
 /* replaces ValidityCheck for EdwardsPoint edwards.rs:393-400, 733-748: ok[i] = 1 iff (aX^2 + Y^2) Z^2 == Z^4 + d X^2 Y^2 */
 int32_t zc_point_is_valid_batch(zc_ctx *ctx, const uint64_t *p, uint8_t *ok, size_t n);
 int32_t zc_point_is_valid_batch_dev(zc_ctx *ctx, const uint64_t *p, uint8_t *ok, size_t n);

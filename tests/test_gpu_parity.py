@@ -334,6 +334,36 @@ def test_ristretto_decompress_and_validity(zc, oracle, kats):
     assert [int(x) for x in got] == [oracle.pt_is_valid(q) for q in Q] and not got.any()
 
 
+def test_ristretto_elligator_and_from_uniform_bytes(zc, oracle, kats):
+    """elligator_ristretto_flavor ristretto.rs:430-471 and from_uniform_bytes :493-507, all 20 limbs vs the oracle: the
+    reference's Sage vector (elligator_vs_ristretto_sage :678-720), r0 = 0 / 1 / p-1, canonical and non-canonical inputs
+    (from_bytes keeps 256 bits, field.rs:563-587), random 64-byte strings."""
+    b = zc.batch
+    r = kats["ristretto"]
+    r0 = oracle.fe_from_bytes(bytes.fromhex(r["elligator_input_hex"]))
+    p = 2**252 + 27742317777372353535851937790883648493
+    rng = np.random.default_rng(7)
+    ins = [r0, oracle.int_to_limbs(0), oracle.int_to_limbs(1), oracle.int_to_limbs(p - 1), oracle.int_to_limbs(2)]
+    ins += list(oracle.synth_fe(SEED, 78, 0, 300))
+    for _ in range(100):                                                    # values in [p, 2^256): limbs as from_bytes builds them
+        v = int.from_bytes(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), "little") | (1 << 255)
+        ins.append(np.array([(v >> (52 * i)) & ((1 << 52) - 1) for i in range(4)] + [v >> 208], dtype=np.uint64))
+    ins = np.array(ins, dtype=np.uint64)
+    got = b.ristretto_elligator(ins)
+    for i in range(ins.shape[0]):
+        assert np.array_equal(got[i], oracle.ris_elligator(ins[i])), i
+    assert b.point_is_valid(got).all()
+    want0 = oracle.ris_elligator(r0)
+    assert oracle.ris_compress(got[0]) == oracle.ris_compress(want0)
+    data = rng.integers(0, 256, size=(300, 64), dtype=np.uint8)
+    data[0] = 0
+    data[1] = 0xff
+    pts = b.ristretto_from_uniform_bytes(data)
+    for i in range(data.shape[0]):
+        assert np.array_equal(pts[i], oracle.ris_from_uniform_bytes(data[i])), i
+    assert b.point_is_valid(pts).all()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # config 5: MSM (derived oracle: fold of double_and_add, SURVEY.md 8c)
 # ---------------------------------------------------------------------------------------------------------
