@@ -94,8 +94,12 @@ __host__ __device__ constexpr int short_window_sub_bits(int c, int w) {
   return ba < c - 1 ? (c - 1) - ba : 0;
 }
 
+// Which of this rank's tasks (local index tl, or -1) takes window w, and for which point range [p0, p1).  A task is a
+// window (all points) today; the range exists so that a window can be split by points between ranks.
+struct WinMap { int16_t tl[MAX_WINDOWS]; uint32_t p0[MAX_WINDOWS], p1[MAX_WINDOWS]; };
+
 template <int C>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, int rank, int nranks,
+__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, const WinMap map,
                                                          int32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
   constexpr int NWIN = (256 + C - 1) / C;
   constexpr uint32_t HALF = 1u << (C - 1), MASK = (1u << C) - 1u, NB = HALF;
@@ -123,16 +127,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restr
       carry = c1 | (v[k] < t);
     }
   }
-  int wl = 0;
 #pragma unroll
   for (int w = 0; w < NWIN; w++) {
-    if (w % nranks == rank) {
+    const int wl = map.tl[w];
+    if (wl >= 0) {
       const int bit = C * w, word = bit >> 6, sh = bit & 63;
       uint64_t x = v[word] >> sh;
       if (sh + C > 64 && word + 1 < 5) x |= v[word + 1] << (64 - sh);
       const int32_t d = (int32_t)((uint32_t)x & MASK) - (int32_t)HALF;
-      int32_t key = d;                                        // sign * (bucket slot + 1), 0 = skip
-      if (d != 0) {
+      int32_t key = 0;                                        // sign * (bucket slot + 1), 0 = skip
+      if (d != 0 && i >= map.p0[w] && i < map.p1[w]) {
         uint32_t slot = (uint32_t)(d < 0 ? -d : d) - 1u;
         const int SUB = short_window_sub_bits(C, w);      // top window(s) of a 250-bit scalar: few distinct digits
         if (SUB > 0) slot = ((slot << SUB) | ((uint32_t)i & ((1u << SUB) - 1u))) & (NB - 1u);
@@ -140,7 +144,6 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restr
         atomicAdd(&hist[(size_t)wl * NB + slot], 1u);
       }
       digits[(size_t)wl * n + i] = key;
-      wl++;
     }
   }
 }
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restr
 // entry) or T slot (run containing its last entry, when that is a different run).  msm_fix_kernel then stitches the
 // buckets that span several segments.  Every thread does the same number of additions, whatever the digit
 // distribution (a top window with few, heavy buckets used to serialise thousands of additions in one thread).
-constexpr int SEG = 32;
+constexpr int SEG_MAX = 32;           // segment length is 8, 16 or 32 (chosen per call from the amount of work)
 constexpr int ACC_TPB = 128;
 
 // Operands are gathered into shared memory with cp.async (no register staging) one entry ahead of the addition that
@@ -262,10 +265,10 @@ __device__ __forceinline__ Pt staged_to_pt(const uint4* __restrict__ q, bool neg
 
 __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
                                                                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                               size_t n_pad, int nseg, int nwl, int nb,
+                                                               size_t n_pad, int nseg, int seg, int nwl, int nb,
                                                                uint32_t* __restrict__ buckets, uint32_t* __restrict__ partH,
                                                                uint32_t* __restrict__ partT) {
-  __shared__ uint32_t idx_s[SEG * ACC_TPB];
+  __shared__ uint32_t idx_s[SEG_MAX * ACC_TPB];
   __shared__ __align__(16) uint4 stage[ACC_NBUF][8 * ACC_TPB];
   const int tx = threadIdx.x;
   size_t g = (size_t)blockIdx.x * ACC_TPB + tx;
@@ -275,13 +278,13 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
   const uint32_t* woffs = offs + wl * nb;
   const uint32_t* whist = hist + wl * nb;
   const uint32_t nnz = woffs[nb - 1] + whist[nb - 1];
-  const uint32_t start = s * SEG;
+  const uint32_t start = s * (uint32_t)seg;
   if (start >= nnz) return;
-  const uint32_t end = min(start + SEG, nnz);
+  const uint32_t end = min(start + (uint32_t)seg, nnz);
   {
     const uint4* src = reinterpret_cast<const uint4*>(sorted + wl * n_pad + start);
-#pragma unroll
-    for (int j = 0; j < SEG / 4; j++) {
+#pragma unroll 2
+    for (int j = 0; j < seg / 4; j++) {
       uint4 v = src[j];
       idx_s[(4 * j + 0) * ACC_TPB + tx] = v.x; idx_s[(4 * j + 1) * ACC_TPB + tx] = v.y;
       idx_s[(4 * j + 2) * ACC_TPB + tx] = v.z; idx_s[(4 * j + 3) * ACC_TPB + tx] = v.w;
@@ -343,13 +346,13 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
 // writes them into buckets[].
 constexpr int FIX_INLINE = 6;
 __global__ void __launch_bounds__(256) msm_fixq_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                       int nwl, int nb, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+                                                       int seg, int nwl, int nb, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
   size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= (size_t)nwl * nb) return;
   const uint32_t cnt = hist[g];
   if (cnt == 0) return;
   const uint32_t o = offs[g], e = o + cnt;
-  const uint32_t s_first = o / SEG, s_last = (e - 1) / SEG;
+  const uint32_t s_first = o / (uint32_t)seg, s_last = (e - 1) / (uint32_t)seg;
   if (s_last - s_first + 1 > FIX_INLINE) {
     uint32_t slot = atomicAdd(heavy_count, 1u);
     heavy_list[slot] = (uint32_t)g;
@@ -364,19 +367,20 @@ __device__ __noinline__ Pt pt_double_ni(Pt p) { return pt_double_fast(p); }
 
 struct BucketSrc {                  // where a group's buckets live (all pointers relative to the group's first window)
   const uint32_t *offs, *hist, *partH, *partT, *buckets;
-  int nseg, nb;
+  int nseg, nb, seg;
 };
 // bucket g of the group, stitched from its segment partials when it spans a few segments
 __device__ __forceinline__ Pt load_bucket(const BucketSrc& b, size_t g) {
+  const int seg = b.seg;
   const uint32_t cnt = b.hist[g];
   if (cnt == 0) return pt_identity_mont();
   const uint32_t o = b.offs[g], e = o + cnt;
-  const uint32_t s_first = o / SEG, s_last = (e - 1) / SEG;
+  const uint32_t s_first = o / (uint32_t)seg, s_last = (e - 1) / (uint32_t)seg;
   if (s_first == s_last || s_last - s_first + 1 > FIX_INLINE) return ld_pt(b.buckets + 32 * g);
   const size_t wl = g / b.nb;
   const uint32_t* H = b.partH + 32 * (wl * b.nseg);
   const uint32_t* T = b.partT + 32 * (wl * b.nseg);
-  Pt acc = ld_pt((o == s_first * SEG ? H : T) + 32 * (size_t)s_first);
+  Pt acc = ld_pt((o == s_first * (uint32_t)seg ? H : T) + 32 * (size_t)s_first);
   for (uint32_t s2 = s_first + 1; s2 <= s_last; s2++) acc = pt_add_ni(acc, ld_pt(H + 32 * (size_t)s2));
   return acc;
 }
@@ -399,7 +403,7 @@ __device__ __forceinline__ Pt warp_sum_pt(Pt v) {
 }
 
 __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                        int nseg, int nb, const uint32_t* __restrict__ partH,
+                                                        int nseg, int seg, int nb, const uint32_t* __restrict__ partH,
                                                         const uint32_t* __restrict__ partT, uint32_t* __restrict__ buckets,
                                                         const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
   const uint32_t nheavy = *heavy_count;
@@ -408,13 +412,13 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restri
     const uint32_t g = heavy_list[h];
     const size_t wl = g / (uint32_t)nb;
     const uint32_t o = offs[g], e = o + hist[g];
-    const uint32_t s_first = o / SEG, s_last = (e - 1) / SEG;
+    const uint32_t s_first = o / (uint32_t)seg, s_last = (e - 1) / (uint32_t)seg;
     const uint32_t* H = partH + 32 * (wl * nseg);
     const uint32_t* T = partT + 32 * (wl * nseg);
     Pt acc = pt_identity_mont();
     bool have = false;
     for (uint32_t s = s_first + lane; s <= s_last; s += 32) {
-      Pt v = ld_pt(((s == s_first && o != s_first * SEG) ? T : H) + 32 * (size_t)s);
+      Pt v = ld_pt(((s == s_first && o != s_first * (uint32_t)seg) ? T : H) + 32 * (size_t)s);
       if (!have) { acc = v; have = true; } else acc = pt_add_ni(acc, v);
     }
     acc = warp_sum_pt(acc);
@@ -694,13 +698,14 @@ __device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
 // of this group's top window.  Each window contributes four components (msm_cube2b):
 //   comp0 2^(A0+a1+a2) + comp1 2^(A0+a1) + comp2 2^A0 + comp3.
 //   for i in 0..ng-1 (group windows in descending order):
-//     if (i > 0) acc = 2^(gap_in - A0 - a1 - a2) acc
+//     if (i > 0) acc = 2^(gaps.pre[i]) acc        (= c * (window distance) - A0 - a1 - a2)
 //     acc += comp0;  acc = 2^a2 acc;  acc += comp1;  acc = 2^a1 acc;  acc += comp2;  acc = 2^A0 acc;  acc += comp3
 //   acc = 2^gap_post acc          (gap_post already excludes A0 + a1 + a2 when another group follows)
 // first != 0: acc starts as the identity.  out52 != nullptr: also store the result in the ABI layout.
 // drop0: the first window's comp3 carries weight 1 on every bucket (sub-bucketed short window): A0 - drop0 doublings.
+struct ChainGaps { int pre[8]; };     // doublings before window i of the group (i >= 1), beyond the A0 + a1 + a2 inside it
 __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ comp, int ng, int first, int a1, int a2, int drop0,
-                                                       int gap_in, int gap_post, uint32_t* __restrict__ acc_io,
+                                                       const ChainGaps gaps, int gap_post, uint32_t* __restrict__ acc_io,
                                                        uint64_t* __restrict__ out52) {
   const int lane = threadIdx.x;
   const int q = lane & 3, qbase = lane & ~3;
@@ -711,7 +716,7 @@ __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restric
     const uint32_t* cw = comp - 128 * (ptrdiff_t)i;          // windows in descending order
 #pragma unroll 1
     for (int part = 0; part < 4; part++) {
-      int nd = part == 0 ? (i > 0 ? gap_in - A0 - a1 - a2 : 0) : (part == 1 ? a2 : (part == 2 ? a1 : (i == 0 ? A0 - drop0 : A0)));
+      int nd = part == 0 ? (i > 0 ? gaps.pre[i] : 0) : (part == 1 ? a2 : (part == 2 ? a1 : (i == 0 ? A0 - drop0 : A0)));
 #pragma unroll 1
       for (int j = 0; j < nd; j++) c = quad_double(c, q, qbase);
       c = quad_add(c, ld_pt(cw + 32 * part), q, qbase);
@@ -740,8 +745,17 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
   if (n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "n exceeds 2^31 - 1");
   const int nwin = (256 + c - 1) / c;
   const int nb = 1 << (c - 1);
+  // Tasks of this rank, ascending by window: the windows w = rank (mod nranks) over all n points.  (A task may also be a
+  // point range of a window -- msm_digits_kernel honours [p0, p1).  Splitting the low windows between rank pairs, so that
+  // no rank's last window needs more than c (nranks/2 - 1) doublings, was measured at 8 ranks and did not pay: the third
+  // bucket reduction per rank costs what the shorter chain saves.)
+  struct Task { int w; uint32_t p0, p1; };
+  Task tasks[MAX_WINDOWS];
   int nwl = 0;
-  for (int w = 0; w < nwin; w++) if (w % nranks == rank) nwl++;
+  for (int w = 0; w < nwin; w++) if (w % nranks == rank) tasks[nwl++] = {w, 0u, (uint32_t)n};
+  WinMap wmap;
+  for (int w = 0; w < MAX_WINDOWS; w++) { wmap.tl[w] = -1; wmap.p0[w] = 0; wmap.p1[w] = 0; }
+  for (int t = 0; t < nwl; t++) { wmap.tl[tasks[t].w] = (int16_t)t; wmap.p0[tasks[t].w] = tasks[t].p0; wmap.p1[tasks[t].w] = tasks[t].p1; }
 
   uint64_t *partial = exchange ? nullptr : out_point_dev;
   if (exchange) {
@@ -758,11 +772,16 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o = 0;
     size_t o_cached = o; o = align_up(o + n * 128, 256);
     size_t o_digits = o; o = align_up(o + (size_t)nwl * n * 4, 256);
-    const size_t n_pad = align_up(n, SEG);
-    const int nseg = (int)(n_pad / SEG);
+    // Segment length, per task group: 32 when the group holds >= 2^22 entries, 16 below that, 8 for <= 2^19 -- less work
+    // gets shorter segments so that the accumulation still fills the GPU (one window of 2^20 points in 32-entry segments
+    // is 256 CTAs of 32 serial additions each: latency-bound at 190 us).  Shorter segments mean more partials to stitch
+    // per bucket (a 64-entry bucket spans 8-9 segments of 8 and would go to the one-warp-per-bucket heavy path), hence
+    // not always 8.  The partial-slot arrays are laid out for the shortest segment.
+    const size_t n_pad = align_up(n, SEG_MAX);
+    const int nseg_alloc = (int)(n_pad / 8);
     size_t o_sorted = o; o = align_up(o + (size_t)nwl * n_pad * 4 + 256, 256);
-    size_t o_partH = o; o = align_up(o + (size_t)nwl * nseg * 128, 256);
-    size_t o_partT = o; o = align_up(o + (size_t)nwl * nseg * 128, 256);
+    size_t o_partH = o; o = align_up(o + (size_t)nwl * nseg_alloc * 128, 256);
+    size_t o_partT = o; o = align_up(o + (size_t)nwl * nseg_alloc * 128, 256);
     size_t o_heavy = o; o = align_up(o + 256 * MAX_GROUPS + (size_t)nwl * nb * 4, 256);
     size_t o_hist = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_offs = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
@@ -779,7 +798,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o_pm1 = o;  o = align_up(o + (size_t)nwl * nblk * nw1 * 128, 256);
     size_t o_pm0 = o;  o = align_up(o + (size_t)nwl * nblk * 32 * 128, 256);
     size_t o_marg = o; o = align_up(o + (size_t)nwl * ntask * 128, 256);
-    size_t o_fold = o; o = align_up(o + (size_t)nb * 128, 256);
+    size_t o_fold = o; o = align_up(o + (size_t)4 * nb * 128, 256);      // one per side stream
     size_t o_acc = o;  o = align_up(o + 128, 256);
     size_t o_comp = o; o = align_up(o + (size_t)nwl * 4 * 128, 256);
     if (o > ctx->msm_ws_bytes) {
@@ -813,14 +832,20 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       // accumulation's grid (observed: 4x longer when they do, and the last group's tail waits for them)
       int prio_lo = 0, prio_hi = 0;
       ZC_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi));
+      // the last group's reduction is on the critical path (high priority); the earlier ones have slack and must not take
+      // SMs from the accumulation that follows them (low priority)
+      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_lo));
+      for (int i = 0; i < 2; i++) ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_extra[i], cudaStreamNonBlocking, prio_lo));
+      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_extra[2], cudaStreamNonBlocking, prio_hi));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, prio_hi));
       for (int i = 0; i < 16; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     }
-    // st: digits, sort, accumulation.  side: operand preparation, then stitch + reduce of each group.  chain: the
+    // st: digits, sort, accumulation.  sides[g % 4]: operand preparation (sides[0]), then stitch + reduce of group g --
+    // the groups' reductions are independent and latency-bound, so they get their own streams and overlap.  chain: the
     // serial window chain.  Events: ev[0] fork, ev[1] prep done, ev[2+g] group g accumulated, ev[6+g] group g reduced,
     // ev[10] chain done.
-    cudaStream_t side = ctx->side_stream, chain = ctx->chain_stream;
+    cudaStream_t sides[4] = {ctx->side_stream, ctx->side_extra[0], ctx->side_extra[1], ctx->side_extra[2]};
+    cudaStream_t side = sides[0], chain = ctx->chain_stream;
 
     // The ~25 launches and the two-stream fork/join of one MSM are recorded once into a CUDA graph and replayed while
     // the call's arguments stay the same (repeated proofs over resident generators): one launch instead of a launch-
@@ -845,7 +870,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       {
         const unsigned grid = (unsigned)((n + 255) / 256);
         switch (c) {
-#define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, rank, nranks, digits, hist); break;
+#define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, wmap, digits, hist); break;
           ZC_DIGITS_CASE(8) ZC_DIGITS_CASE(9) ZC_DIGITS_CASE(10) ZC_DIGITS_CASE(11) ZC_DIGITS_CASE(12)
           ZC_DIGITS_CASE(13) ZC_DIGITS_CASE(14) ZC_DIGITS_CASE(15) ZC_DIGITS_CASE(16)
 #undef ZC_DIGITS_CASE
@@ -857,38 +882,43 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         size_t tot = n * (size_t)nwl;
         msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); nlaunch++; mark(st, 0, "msm_scatter_kernel");
       }
-      // Window groups, top-down.  Local window wl is global window rank + nranks * wl.  After a group's buckets are
+      // Task groups, top-down (local index wl ascends with the window index).  After a group's buckets are
       // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
       // next group's top window (or, after the last group, by 2^(c * rank)) while the main stream accumulates the next group.
       const int ngroups = nwl < MAX_GROUPS ? nwl : MAX_GROUPS;
       int hi = nwl;
       for (int g = 0; g < ngroups; g++) {
+        side = (g == ngroups - 1) ? sides[3] : sides[g % 3];
         const int gsz = (hi + (ngroups - g) - 1) / (ngroups - g);
         const int lo = hi - gsz;
+        size_t group_entries = 0;
+        for (int wl = lo; wl < hi; wl++) group_entries += tasks[wl].p1 - tasks[wl].p0;
+        const int seg = group_entries >= ((size_t)1 << 22) ? 32 : (group_entries > ((size_t)1 << 19) ? 16 : 8);
+        const int nseg = (int)(n_pad / seg);
         const size_t tot = (size_t)gsz * nb;
         const size_t tseg = (size_t)gsz * nseg;
         const uint32_t *g_sorted = sorted + (size_t)lo * n_pad, *g_offs = offs + (size_t)lo * nb, *g_hist = hist + (size_t)lo * nb;
-        uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg), *g_partT = partT + 32 * ((size_t)lo * nseg);
+        uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg_alloc), *g_partT = partT + 32 * ((size_t)lo * nseg_alloc);
         uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
         if (g == 0) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
-        msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, gsz, nb, g_buckets, g_partH, g_partT); nlaunch++; mark(st, 0, "msm_accum_kernel");
+        msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT); nlaunch++; mark(st, 0, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
         ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
-        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, side>>>(g_offs, g_hist, gsz, nb, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_fixq_kernel");
-        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_heavy_kernel");
-        const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb};
+        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, side>>>(g_offs, g_hist, seg, gsz, nb, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_fixq_kernel");
+        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, seg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_heavy_kernel");
+        const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb, seg};
         // A short (top) window spreads each digit over 2^sub sub-buckets.  sub == A0: the sub-bucket index is exactly the
         // lane digit of the cube, which then simply carries weight 0 (drop).  Otherwise sum the sub-buckets back first.
         uint32_t raw_mask = 0; int drop_wl = -1;
         for (int wl = lo; wl < hi; wl++) {
-          const int sub = short_window_sub_bits(c, rank + nranks * wl);
+          const int sub = short_window_sub_bits(c, tasks[wl].w);
           if (sub == A0 && g == 0 && wl == hi - 1) drop_wl = wl - lo;
           else if (sub > 0) {
             raw_mask |= 1u << (wl - lo);
-            msm_fold_kernel<<<(unsigned)(((nb >> sub) + 3) / 4), 128, 0, side>>>(src, (size_t)(wl - lo), sub, folded); nlaunch++; mark(side, 1, "msm_fold_kernel");
-            msm_unfold_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, side>>>(folded, nb, nb >> sub, buckets + 32 * ((size_t)wl * nb)); nlaunch++; mark(side, 1, "msm_unfold_kernel");
+            msm_fold_kernel<<<(unsigned)(((nb >> sub) + 3) / 4), 128, 0, side>>>(src, (size_t)(wl - lo), sub, folded + (size_t)(g == ngroups - 1 ? 3 : g % 3) * nb * 32); nlaunch++; mark(side, 1, "msm_fold_kernel");
+            msm_unfold_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, side>>>(folded + (size_t)(g == ngroups - 1 ? 3 : g % 3) * nb * 32, nb, nb >> sub, buckets + 32 * ((size_t)wl * nb)); nlaunch++; mark(side, 1, "msm_unfold_kernel");
           }
         }
         const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
@@ -903,8 +933,12 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[6 + g], side));
         ZC_CUDA(ctx, cudaStreamWaitEvent(chain, ctx->ev[6 + g], 0));
         const bool last = (g == ngroups - 1);
-        msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, drop0, c * nranks,
-                                             last ? c * rank : c * nranks - A0 - a1 - a2, acc, last ? partial : nullptr); nlaunch++; mark(chain, 2, "msm_chain_kernel");
+        ChainGaps gaps;
+        for (int i = 0; i < 8; i++) gaps.pre[i] = 0;
+        for (int i = 1; i < gsz; i++) gaps.pre[i] = c * (tasks[hi - i].w - tasks[hi - 1 - i].w) - A0 - a1 - a2;
+        const int gap_post = last ? c * tasks[lo].w : c * (tasks[lo].w - tasks[lo - 1].w) - A0 - a1 - a2;
+        msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, drop0, gaps,
+                                             gap_post, acc, last ? partial : nullptr); nlaunch++; mark(chain, 2, "msm_chain_kernel");
         hi = lo;
       }
       ZC_CUDA(ctx, cudaEventRecord(ctx->ev[10], chain));

@@ -19,6 +19,12 @@ def windows_of_rank(window_bits, rank, nranks):
     return [w for w in range(num_windows(window_bits)) if w % nranks == rank]
 
 
+def tasks_of_rank(window_bits, rank, nranks, n):
+    """The (window, p0, p1) tasks of a rank, ascending by window -- the plan csrc/zc_msm.cu builds: the windows
+    w = rank (mod nranks) over all n points.  Every (window, point) pair is owned by exactly one rank."""
+    return [(w, 0, n) for w in windows_of_rank(window_bits, rank, nranks)]
+
+
 def signed_digits(scalar_int, window_bits):
     """d_w in [-2^(c-1), 2^(c-1)) with sum_w d_w 2^(c w) == scalar (same recoding as msm_digits_kernel)."""
     c = window_bits

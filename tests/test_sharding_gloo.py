@@ -29,6 +29,55 @@ def test_window_plan():
             assert all(-(1 << (c - 1)) <= x < (1 << (c - 1)) for x in d)
 
 
+def test_task_plan_covers_every_window_point_once():
+    for c, R, n in [(16, 8, 10), (16, 8, 7), (16, 4, 5), (16, 2, 5), (16, 1, 3), (8, 16, 6), (13, 8, 4), (16, 16, 4)]:
+        seen = {}
+        for r in range(R):
+            t = sharding.tasks_of_rank(c, r, R, n)
+            assert [w for w, _, _ in t] == sorted(w for w, _, _ in t)
+            for w, p0, p1 in t:
+                for i in range(p0, p1):
+                    assert (w, i) not in seen, (c, R, w, i)
+                    seen[(w, i)] = r
+        assert len(seen) == sharding.num_windows(c) * n
+    assert all(len(sharding.tasks_of_rank(16, r, 8, 100)) == 2 for r in range(8))
+
+
+def _model_partial(o, P, S, c, rank, world):
+    """One rank's partial point: Horner over all windows, adding only the (window, point range) tasks it owns."""
+    n = P.shape[0]
+    digs = [sharding.signed_digits(sharding.limbs_to_int(S[i]), c) for i in range(n)]
+    nwin = sharding.num_windows(c)
+    mine = {w: (p0, p1) for w, p0, p1 in sharding.tasks_of_rank(c, rank, world, n)}
+    acc, started = o.pt_identity(), False
+    for w in range(nwin - 1, -1, -1):
+        if started:
+            for _ in range(c):
+                acc = o.pt_double(acc)
+        if w in mine:
+            ws = o.pt_identity()
+            for i in range(*mine[w]):
+                d = digs[i][w]
+                if d:
+                    t = o.pt_double_and_add(P[i], o.int_to_limbs(abs(d)))
+                    ws = o.pt_add(ws, o.pt_neg(t) if d < 0 else t)
+            acc = o.pt_add(acc, ws)
+            started = True
+    return acc
+
+
+def test_plan_model_8_ranks(oracle):
+    """The 8-rank plan folds to the naive MSM -- the oracle as the group."""
+    o = oracle
+    n, c, world = 5, 16, 8
+    P = o.pt_scalar_mul_batch(np.tile(synth.BASEPOINT, (n, 1)), synth.synth_scalar(210, 0, n))
+    S = synth.synth_scalar(211, 0, n)
+    total = _model_partial(o, P, S, c, 0, world)
+    for r in range(1, world):
+        total = o.pt_add(total, _model_partial(o, P, S, c, r, world))
+    assert o.pt_eq(total, o.msm_naive(P, S))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -43,23 +92,7 @@ def _worker(rank, world, port, n, c, q):
     base = np.tile(synth.BASEPOINT, (n, 1))
     P = o.pt_scalar_mul_batch(base, synth.synth_scalar(200, 0, n))
     S = synth.synth_scalar(201, 0, n)
-    digs = [sharding.signed_digits(sharding.limbs_to_int(S[i]), c) for i in range(n)]
-    nwin = sharding.num_windows(c)
-    acc, started = o.pt_identity(), False
-    mine = set(sharding.windows_of_rank(c, rank, world))
-    for w in range(nwin - 1, -1, -1):                      # Horner over all windows, adding only the owned ones
-        if started:
-            for _ in range(c):
-                acc = o.pt_double(acc)
-        if w in mine:
-            ws = o.pt_identity()
-            for i in range(n):
-                d = digs[i][w]
-                if d:
-                    t = o.pt_double_and_add(P[i], o.int_to_limbs(abs(d)))
-                    ws = o.pt_add(ws, o.pt_neg(t) if d < 0 else t)
-            acc = o.pt_add(acc, ws)
-            started = True
+    acc = _model_partial(o, P, S, c, rank, world)
     part = torch.from_numpy(acc.view(np.int64).copy())
     gathered = [torch.zeros(20, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(gathered, part)                          # the ONE exchange step
