@@ -85,6 +85,8 @@ def lib():
         getattr(L, "zc_ristretto_from_uniform_bytes_batch" + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_ristretto_decompress_batch" + suf).argtypes = [vp, vp, vp, vp, sz]
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
+    L.zc_msm_prepare_points_dev.argtypes = [vp, vp, sz]
+    L.zc_msm_forget_points.argtypes = [vp]
     L.zc_msm_partial_dev.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
     L.zc_point_fold_dev.argtypes = [vp, vp, sz, vp]
     L.zc_ctx_set_nccl.argtypes = [vp, vp, i32, i32]

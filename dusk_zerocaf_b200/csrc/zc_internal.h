@@ -38,6 +38,10 @@ struct zc_ctx {
   // host-pointer entry points: copy-in / copy-out streams and per-chunk events (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t pipe_ev[2 * ZC_PIPE_MAX_CHUNKS] = {};
+  // MSM operands prepared once for fixed generators (zc_msm_prepare_points_dev)
+  const void *prep_points = nullptr;
+  size_t prep_n = 0;
+  bool prep_valid = false;
   void *basepoint_table = nullptr;  // fixed-base table (zc_fixed.cu), built on first use
   void *msm_graph_exec = nullptr;   // cudaGraphExec_t of the last MSM configuration
   zc_msm_key msm_key = {};

@@ -733,6 +733,13 @@ __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restric
   }
 }
 
+// development aid (ZC_MSM_TRACE=2): device-side timestamps between the kernels of the captured graph
+__global__ void msm_stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -803,7 +810,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o_comp = o; o = align_up(o + (size_t)nwl * 4 * 128, 256);
     if (o > ctx->msm_ws_bytes) {
       if (ctx->msm_ws) ZC_CUDA(ctx, cudaFree(ctx->msm_ws));
-      ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0;
+      ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0; ctx->prep_valid = false;
       ZC_CUDA(ctx, cudaMalloc(&ctx->msm_ws, o));
       ctx->msm_ws_bytes = o;
     }
@@ -850,12 +857,29 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     // The ~25 launches and the two-stream fork/join of one MSM are recorded once into a CUDA graph and replayed while
     // the call's arguments stay the same (repeated proofs over resident generators): one launch instead of a launch-
     // latency-bound sequence -- at 8 ranks the per-rank kernels are short enough for launch gaps to rival the math.
+    // prepared points (zc_msm_prepare_points_dev): the cached operands at the head of the workspace are reused
+    const bool use_prepared = points && ctx->prep_points == (const void*)points && ctx->prep_n == n;
+    if (use_prepared && !ctx->prep_valid) {                    // the workspace was reallocated since: prepare again
+      msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(points, cached, n); ctx->launches++;
+      ctx->prep_valid = true;
+    }
     uint64_t nlaunch = 0;
-    // ZC_MSM_TRACE=1: no graph, a timing event after every kernel, timeline printed to stderr (development aid)
-    static const bool trace = getenv("ZC_MSM_TRACE") != nullptr;
+    // ZC_MSM_TRACE=1: no graph, a timing event after every kernel, timeline printed to stderr (development aid).
+    // ZC_MSM_TRACE=2: the graph as usual, with a one-thread %globaltimer stamp after every kernel; timeline printed
+    // after each call (synchronises).
+    static const int trace_mode = getenv("ZC_MSM_TRACE") ? atoi(getenv("ZC_MSM_TRACE")) : 0;
+    const bool trace = trace_mode == 1;
     struct Mark { cudaEvent_t ev; const char* name; int stream; };
     std::vector<Mark> marks;
+    static unsigned long long* stamp_buf = nullptr;
+    static std::vector<std::pair<const char*, int>> stamp_names;
+    if (trace_mode == 2 && !stamp_buf) cudaMalloc(&stamp_buf, 256 * sizeof(unsigned long long));
+    int nstamp = 0;
     auto mark = [&](cudaStream_t s_, int sid, const char* name) {
+      if (trace_mode == 2) {
+        if (nstamp < 256) { msm_stamp_kernel<<<1, 1, 0, s_>>>(stamp_buf + nstamp); if ((int)stamp_names.size() <= nstamp) stamp_names.push_back({name, sid}); nstamp++; }
+        return;
+      }
       if (!trace) return;
       cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); marks.push_back({e, name, sid});
     };
@@ -863,10 +887,12 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       mark(st, 0, "start");
       ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwl * nb * 4, st));
       ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
-      ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-      ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[0], 0));
-      msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++; mark(side, 1, "msm_prep_kernel");
-      ZC_CUDA(ctx, cudaEventRecord(ctx->ev[1], side));
+      if (!use_prepared) {
+        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+        ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[0], 0));
+        msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++; mark(side, 1, "msm_prep_kernel");
+        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[1], side));
+      }
       {
         const unsigned grid = (unsigned)((n + 255) / 256);
         switch (c) {
@@ -900,7 +926,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         const uint32_t *g_sorted = sorted + (size_t)lo * n_pad, *g_offs = offs + (size_t)lo * nb, *g_hist = hist + (size_t)lo * nb;
         uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg_alloc), *g_partT = partT + 32 * ((size_t)lo * nseg_alloc);
         uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
-        if (g == 0) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
+        if (g == 0 && !use_prepared) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
         msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT); nlaunch++; mark(st, 0, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
@@ -946,7 +972,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       ZC_CUDA(ctx, cudaGetLastError());
       return ZC_OK;
     };
-    const zc_msm_key key = {points, scalars, n, c, rank, nranks, 0, partial, ctx->msm_ws};
+    const zc_msm_key key = {points, scalars, n, c, rank, nranks, use_prepared ? 1 : 0, partial, ctx->msm_ws};
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     ZC_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
     if (cap != cudaStreamCaptureStatusNone || trace) {
@@ -983,6 +1009,14 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       ZC_CUDA(ctx, cudaGraphLaunch(exec, st));
       ctx->launches += nlaunch;
     }
+    if (trace_mode == 2 && stamp_buf && !stamp_names.empty()) {
+      cudaStreamSynchronize(st);
+      std::vector<unsigned long long> h(stamp_names.size());
+      cudaMemcpy(h.data(), stamp_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[zc_msm graph timeline] n=%zu c=%d rank %d/%d\n", n, c, rank, nranks);
+      for (size_t i = 1; i < h.size(); i++)
+        fprintf(stderr, "  %8.1f us  s%d  %s\n", (double)(h[i] - h[0]) * 1e-3, stamp_names[i].second, stamp_names[i].first);
+    }
   }
 
   if (exchange) {
@@ -995,6 +1029,31 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
 }
 
 extern "C" {
+
+int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points, size_t n) {
+  if (!ctx) return ZC_ERR_NULL;
+  ZC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!points || n == 0) return zc_fail(ctx, ZC_ERR_NULL, "null / empty points");
+  if (n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "n exceeds 2^31 - 1");
+  const size_t need = align_up(n * 128, 256);
+  if (need > ctx->msm_ws_bytes) {
+    if (ctx->msm_ws) ZC_CUDA(ctx, cudaFree(ctx->msm_ws));
+    ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0;
+    ZC_CUDA(ctx, cudaMalloc(&ctx->msm_ws, need));
+    ctx->msm_ws_bytes = need;
+  }
+  msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(points, (uint32_t*)ctx->msm_ws, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  ctx->prep_points = points; ctx->prep_n = n; ctx->prep_valid = true;
+  return ZC_OK;
+}
+
+int32_t zc_msm_forget_points(zc_ctx *ctx) {
+  if (!ctx) return ZC_ERR_NULL;
+  ctx->prep_points = nullptr; ctx->prep_n = 0; ctx->prep_valid = false;
+  return ZC_OK;
+}
 
 int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev) {
   if (!ctx) return ZC_ERR_NULL;

@@ -162,6 +162,13 @@ int32_t zc_point_is_valid_batch_dev(zc_ctx *ctx, const uint64_t *p, uint8_t *ok,
 int32_t zc_msm(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point);
 int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev);
 
+/* Fixed generators (bulletproofs G_i, H_i): prepare the MSM operands once.  After zc_msm_prepare_points_dev(points, n),
+ * zc_msm_dev / zc_msm_partial_dev / zc_msm_sharded_dev calls with the SAME device pointer and n reuse the cached
+ * (Y+X, Y-X, Z, 2dT) array kept in the context instead of rebuilding it per call.  The caller must not modify points[]
+ * in place while it is prepared; zc_msm_forget_points drops the cache.  Results are unchanged. */
+int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t n);
+int32_t zc_msm_forget_points(zc_ctx *ctx);
+
 /* Bucket-window-sharded MSM: a collective, every rank calls it with the same (points, scalars, n, window_bits), all
  * resident on its own device.  Rank r accumulates windows w = r (mod nranks), scales its window sums and folds them to
  * one partial point; the partial points are exchanged with ONE ncclAllGather on the context's stream and folded in rank

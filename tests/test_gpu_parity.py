@@ -429,6 +429,29 @@ def test_msm_sharding_partials_fold_to_full(zc, oracle):
 # ---------------------------------------------------------------------------------------------------------
 # host-side mirror types read like the reference's own tests
 # ---------------------------------------------------------------------------------------------------------
+def test_msm_prepared_points(zc, oracle):
+    """zc_msm_prepare_points_dev: same result with the cached operands, for several scalar vectors, window sizes (the
+    workspace grows -> the cache is rebuilt) and after forgetting."""
+    import torch
+    n = 5000
+    P = synth_points(oracle, 80, n)
+    ctx = zc.default_context()
+    L = ctx._L
+    dP = torch.from_numpy(P.view(np.int64)).cuda()
+    out = torch.zeros(20, dtype=torch.int64, device="cuda")
+    ctx.check(L.zc_msm_prepare_points_dev(ctx._h, dP.data_ptr(), n))
+    for k, c in enumerate((16, 12, 16, 9)):
+        s = oracle.synth_scalar(SEED, 81 + k, 0, n)
+        dS = torch.from_numpy(s.view(np.int64)).cuda()
+        ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, out.data_ptr()))
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8)), (k, c)
+    ctx.check(L.zc_msm_forget_points(ctx._h))
+    ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
+
+
 def test_operator_surface(zc, kats, oracle):
     A, B = zc.FieldElement(F(kats, "A")), zc.FieldElement(F(kats, "B"))
     assert (A * B) == zc.FieldElement(F(kats, "A_TIMES_B"))

@@ -18,6 +18,7 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--rank", type=int, default=0)
 ap.add_argument("--nranks", type=int, default=1)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--prepared", action="store_true")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -32,6 +33,8 @@ ctx.check(L.zc_point_scalar_mul_batch_dev(ctx._h, base.data_ptr(), sc.data_ptr()
 S = torch.from_numpy(synth.synth_scalar(102, 0, n).view(np.int64)).to(dev)
 out = torch.zeros(20, dtype=torch.int64, device=dev)
 ctx.sync()
+if a.prepared:
+    ctx.check(L.zc_msm_prepare_points_dev(ctx._h, P.data_ptr(), n))
 for it in range(a.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
