@@ -8,7 +8,7 @@
 
 #include "../../include/zerocaf_b200.h"
 
-#define ZC_PIPE_MAX_CHUNKS 64
+#define ZC_PIPE_MAX_CHUNKS 512
 
 // arguments an instantiated MSM graph was recorded with (zc_msm.cu)
 struct zc_msm_key {
