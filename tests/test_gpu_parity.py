@@ -452,6 +452,29 @@ def test_msm_prepared_points(zc, oracle):
     assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
 
 
+def test_abi_error_convention(zc, oracle):
+    """Status codes instead of panics (include/zerocaf_b200.h): argument errors > 0 with a message, n = 0 is a no-op,
+    and a failed call leaves the context usable."""
+    import torch
+    ctx = zc.default_context()
+    L = ctx._L
+    a = torch.zeros((4, 5), dtype=torch.int64, device="cuda")
+    out = torch.zeros((4, 20), dtype=torch.int64, device="cuda")
+    assert L.zc_fe_mul_batch_dev(ctx._h, a.data_ptr(), None, a.data_ptr(), 4) == 1                      # ZC_ERR_NULL
+    assert b"null" in L.zc_last_error_string(ctx._h)
+    assert L.zc_fe_mul_batch_dev(ctx._h, None, None, None, 0) == 0                                      # empty batch
+    assert L.zc_point_scalar_mul_batch_dev(ctx._h, out.data_ptr(), a.data_ptr(), out.data_ptr(), 4, 7) == 3   # ZC_ERR_MODE
+    assert L.zc_msm_dev(ctx._h, out.data_ptr(), a.data_ptr(), 4, 17, out.data_ptr()) == 3               # window out of range
+    assert L.zc_msm_dev(ctx._h, out.data_ptr(), a.data_ptr(), 4, 7, out.data_ptr()) == 3
+    assert L.zc_fe_mul_batch_dev(ctx._h, a.data_ptr(), a.data_ptr(), a.data_ptr(), (1 << 31) + 1) == 2  # ZC_ERR_SIZE
+    assert L.zc_msm_sharded_dev(ctx._h, out.data_ptr(), a.data_ptr(), 4, 16, out.data_ptr()) == 5       # no communicator
+    with pytest.raises(zc.ZerocafError):
+        ctx.check(L.zc_msm_dev(ctx._h, None, None, 4, 16, out.data_ptr()))
+    # still usable
+    one = np.tile(oracle.int_to_limbs(1), (3, 1))
+    assert np.array_equal(zc.batch.fe_mul(one, one), one)
+
+
 def test_operator_surface(zc, kats, oracle):
     A, B = zc.FieldElement(F(kats, "A")), zc.FieldElement(F(kats, "B"))
     assert (A * B) == zc.FieldElement(F(kats, "A_TIMES_B"))
