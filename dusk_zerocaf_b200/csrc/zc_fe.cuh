@@ -605,6 +605,20 @@ __device__ __forceinline__ Fe fold_product(const uint32_t (&t)[16]) {
   return r;
 }
 
+// a * b mod m from operands already shifted left by SA and SB bits (fe_load52_shl folds the shifts into the unpacking)
+template <class M>
+__device__ __forceinline__ Fe fe_mul_normal_pre(const Fe& a_shl, const Fe& b_shl) {
+  uint32_t t[16];
+  mul_wide_8x8(t, a_shl.w, b_shl.w);
+  return fold_product<M, Shape<M>::S>(t);
+}
+// a^2 mod m from a << SA
+template <class M>
+__device__ __forceinline__ Fe fe_sqr_normal_pre(const Fe& a_shl) {
+  uint32_t t[16];
+  sqr_wide_8(t, a_shl.w);
+  return fold_product<M, 2 * Shape<M>::SA>(t);
+}
 // a * b mod m for canonical NORMAL-form a, b (field.rs:250-262 / scalar.rs:247-258 as a value)
 template <class M>
 __device__ __forceinline__ Fe fe_mul_normal(const Fe& a, const Fe& b) {
@@ -647,6 +661,21 @@ __device__ __forceinline__ void fe_to_limbs52(const Fe& a, uint64_t (&l)[5]) {
   l[2] = ((w1 >> 40) | (w2 << 24)) & MASK;
   l[3] = ((w2 >> 28) | (w3 << 36)) & MASK;
   l[4] = w3 >> 16;
+}
+// value << S (S <= 4; the caller guarantees value << S < 2^256), shifts folded into the unpacking
+template <int S>
+__device__ __forceinline__ Fe fe_load52_shl(const uint64_t* __restrict__ p) {
+  const uint64_t l0 = p[0], l1 = p[1], l2 = p[2], l3 = p[3], l4 = p[4];
+  const uint64_t w0 = (l0 << S) | (l1 << (52 + S));
+  const uint64_t w1 = (l1 >> (12 - S)) | (l2 << (40 + S));
+  const uint64_t w2 = (l2 >> (24 - S)) | (l3 << (28 + S));
+  const uint64_t w3 = (l3 >> (36 - S)) | (l4 << (16 + S));
+  Fe r;
+  r.w[0] = (uint32_t)w0; r.w[1] = (uint32_t)(w0 >> 32);
+  r.w[2] = (uint32_t)w1; r.w[3] = (uint32_t)(w1 >> 32);
+  r.w[4] = (uint32_t)w2; r.w[5] = (uint32_t)(w2 >> 32);
+  r.w[6] = (uint32_t)w3; r.w[7] = (uint32_t)(w3 >> 32);
+  return r;
 }
 __device__ __forceinline__ Fe fe_load52(const uint64_t* __restrict__ p) {
   return fe_from_limbs52(p[0], p[1], p[2], p[3], p[4]);

@@ -23,14 +23,18 @@ __global__ void __launch_bounds__(TPB) fe_op_kernel(const uint64_t* __restrict__
                                                     uint64_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  Fe x = fe_load52(a + 5 * i);
   Fe r;
   if (OP == OP_MUL) {
-    Fe y = fe_load52(b + 5 * i);
-    r = fe_mul_normal<M>(x, y);
-  } else if (OP == OP_SQUARE) {
-    r = fe_sqr_normal<M>(x);
-  } else if (OP == OP_ADD) {
+    r = fe_mul_normal_pre<M>(fe_load52_shl<Shape<M>::SA>(a + 5 * i), fe_load52_shl<Shape<M>::SB>(b + 5 * i));
+    fe_store52(out + 5 * i, r);
+    return;
+  }
+  if (OP == OP_SQUARE) {
+    fe_store52(out + 5 * i, fe_sqr_normal_pre<M>(fe_load52_shl<Shape<M>::SA>(a + 5 * i)));
+    return;
+  }
+  Fe x = fe_load52(a + 5 * i);
+  if (OP == OP_ADD) {
     Fe y = fe_load52(b + 5 * i);
     r = fe_add<M>(x, y);
   } else if (OP == OP_SUB) {
@@ -48,10 +52,11 @@ __global__ void __launch_bounds__(TPB) fe_mul_square_kernel(const uint64_t* __re
                                                             uint64_t* __restrict__ prod, uint64_t* __restrict__ sq, size_t n) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  Fe x = fe_load52(a + 5 * i);
-  Fe y = fe_load52(b + 5 * i);
-  fe_store52(prod + 5 * i, fe_mul_normal<M>(x, y));
-  fe_store52(sq + 5 * i, fe_sqr_normal<M>(x));
+  // operands unpacked straight into their pre-shifted form (SA for a -- shared by the product and the square -- SB for b)
+  const Fe x = fe_load52_shl<Shape<M>::SA>(a + 5 * i);
+  const Fe y = fe_load52_shl<Shape<M>::SB>(b + 5 * i);
+  fe_store52(prod + 5 * i, fe_mul_normal_pre<M>(x, y));
+  fe_store52(sq + 5 * i, fe_sqr_normal_pre<M>(x));
 }
 
 // ---- K2: point add / sub / double / neg on the ABI layout, limb-exact (edwards.rs:440-592) ----------------
