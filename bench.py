@@ -294,6 +294,14 @@ def run_b200(args):
                 return obj[0]
             ctx.init_nccl(rank, world, bcast)
             msm_fn = lambda: ctx.check(L.zc_msm_sharded_dev(ctx._h, P4.data_ptr(), S.data_ptr(), N_MSM, MSM_WINDOW, out_pt.data_ptr()))
+            ms_msm_nccl, _ = timed(msm_fn, 5, 3)                # exchange = ncclAllGather + fold kernel
+            nccl_pt = out_pt.clone()
+
+            def allgather(b):
+                objs = [None] * world
+                dist.all_gather_object(objs, b)
+                return objs
+            ctx.init_peer_mailboxes(rank, world, allgather)     # from here on: NVLink peer stores + flags + fold, one kernel
         else:
             msm_fn = lambda: ctx.check(L.zc_msm_dev(ctx._h, P4.data_ptr(), S.data_ptr(), N_MSM, MSM_WINDOW, out_pt.data_ptr()))
         km = max(5, args.steps // 2)
@@ -301,17 +309,28 @@ def run_b200(args):
         # fixed generators: points prepared once (zc_msm_prepare_points_dev), the timed call only sees new scalars
         ctx.check(L.zc_msm_prepare_points_dev(ctx._h, P4.data_ptr(), N_MSM))
         ms_msm, l_msm = timed(msm_fn, km, 3)
-        identical = True
+        identical, same_elem = True, True
         if world > 1:
             g = [torch.zeros_like(out_pt) for _ in range(world)]
             dist.all_gather(g, out_pt)
             identical = all(bool(torch.equal(g[0], x)) for x in g)
+            # the sharded result is the same group element as this rank's own single-GPU MSM and as the NCCL path's
+            full = torch.zeros(20, dtype=torch.int64, device=dev)
+            ctx.check(L.zc_msm_dev(ctx._h, P4.data_ptr(), S.data_ptr(), N_MSM, MSM_WINDOW, full.data_ptr()))
+            eq = torch.zeros(2, dtype=torch.uint8, device=dev)
+            both = torch.stack([full, nccl_pt])
+            ref2 = torch.stack([out_pt, out_pt])
+            ctx.check(L.zc_ristretto_eq_batch_dev(ctx._h, both.data_ptr(), ref2.data_ptr(), eq.data_ptr(), 2))
+            ctx.sync()
+            same_elem = bool(eq.all().item())
         extra["config5_msm"] = {
             "n_points": N_MSM, "window_bits": MSM_WINDOW, "n_gpus": world, "msm_per_s": km / (ms_msm * 1e-3),
             "ms_per_msm": ms_msm / km, "scaling": "strong", "launches_per_msm": l_msm / km,
             "points_prepared": True, "ms_per_msm_unprepared": ms_msm_raw / km,
-            "all_ranks_identical_bits": identical,
-            "sharding": "bucket-window (w mod N), one ncclAllGather of 160-B partial points + fixed-order fold" if world > 1 else "single GPU",
+            "all_ranks_identical_bits": identical, "matches_single_gpu_and_nccl_path": same_elem,
+            "exchange": "NVLink peer-memory mailboxes: peer stores + flags + tree fold in one kernel" if world > 1 else None,
+            "ms_per_msm_nccl_exchange": (ms_msm_nccl / 5) if world > 1 else None,
+            "sharding": "bucket-window (w mod N), one exchange of the 160-B partial points + fixed-order fold" if world > 1 else "single GPU",
             "hbm_frac": 160.0 * N_MSM / (ms_msm / km * 1e-3) / 1e9 / peak}
 
     cpu = None

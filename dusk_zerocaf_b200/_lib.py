@@ -91,6 +91,8 @@ def lib():
     L.zc_point_fold_dev.argtypes = [vp, vp, sz, vp]
     L.zc_ctx_set_nccl.argtypes = [vp, vp, i32, i32]
     L.zc_nccl_unique_id.argtypes = [vp]
+    L.zc_peer_mailbox_create.argtypes = [vp, vp]
+    L.zc_peer_mailbox_connect.argtypes = [vp, vp, i32, i32]
     L.zc_nccl_comm_init.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.zc_nccl_comm_destroy.argtypes = [vp]
     _lib = L

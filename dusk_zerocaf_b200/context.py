@@ -73,6 +73,17 @@ class Context:
         self.check(self._L.zc_ctx_set_nccl(self._h, comm, int(rank), int(nranks)))
 
 
+    def init_peer_mailboxes(self, rank, nranks, allgather_bytes):
+        """NVLink peer-memory exchange for the sharded MSM.  allgather_bytes(b: bytes) -> list[bytes] in rank order
+        (the host framework's transport, e.g. torch.distributed.all_gather_object)."""
+        buf = (ctypes.c_uint8 * 64)()
+        self.check(self._L.zc_peer_mailbox_create(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+        handles = allgather_bytes(bytes(buf))
+        assert len(handles) == nranks and all(len(h) == 64 for h in handles)
+        allb = (ctypes.c_uint8 * (64 * nranks)).from_buffer_copy(b"".join(handles))
+        self.check(self._L.zc_peer_mailbox_connect(self._h, ctypes.cast(allb, ctypes.c_void_p), int(rank), int(nranks)))
+
+
 _default = None
 
 

@@ -18,6 +18,16 @@ struct zc_msm_key {
   const void *partial, *ws;
 };
 
+// NVLink peer-memory exchange (zc_peer.cu): one mailbox per rank, mapped into every peer with CUDA IPC
+#define ZC_MAX_PEERS 16
+struct zc_mailbox {
+  uint64_t flag[ZC_MAX_PEERS];        // flag[r] = sequence number of the last partial rank r delivered here
+  uint64_t counter;                   // this rank's own exchange count
+  uint64_t pad[15];
+  uint64_t slot[ZC_MAX_PEERS][20];    // slot[r] = rank r's partial point, [u64;20]
+};
+struct zc_peer_ptrs { zc_mailbox* p[ZC_MAX_PEERS]; };
+
 struct zc_ctx {
   int device = 0;
   int sm_count = 148;
@@ -35,6 +45,9 @@ struct zc_ctx {
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;
   void *gather_buf = nullptr;   // nranks * 20 u64, device
+  void *mailbox = nullptr;      // zc_mailbox in this rank's HBM
+  zc_peer_ptrs peers = {};
+  bool peers_connected = false;
   // host-pointer entry points: copy-in / copy-out streams and per-chunk events (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t pipe_ev[2 * ZC_PIPE_MAX_CHUNKS] = {};
@@ -80,6 +93,8 @@ static inline int32_t zc_scratch(zc_ctx *ctx, int slot, size_t bytes, void **out
   return ZC_OK;
 }
 
+// implemented in zc_peer.cu
+int32_t zc_peer_exchange_fold(zc_ctx *ctx, const uint64_t *partial, uint64_t *out);
 // implemented in zc_msm.cu
 int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits,
                    int32_t rank, int32_t nranks, bool exchange, uint64_t *out_point_dev);

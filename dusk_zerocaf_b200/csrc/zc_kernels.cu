@@ -408,6 +408,8 @@ int32_t zc_ctx_destroy(zc_ctx* ctx) {
   if (ctx->msm_ws) cudaFree(ctx->msm_ws);
   if (ctx->basepoint_table) cudaFree(ctx->basepoint_table);
   if (ctx->gather_buf) cudaFree(ctx->gather_buf);
+  if (ctx->peers_connected) for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && ctx->peers.p[r]) cudaIpcCloseMemHandle(ctx->peers.p[r]);
+  if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); for (int i = 0; i < 2 * ZC_PIPE_MAX_CHUNKS; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]); }
   if (ctx->msm_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); cudaStreamSynchronize(ctx->chain_stream); cudaStreamDestroy(ctx->chain_stream); for (int i = 0; i < 3; i++) if (ctx->side_extra[i]) cudaStreamDestroy(ctx->side_extra[i]); }

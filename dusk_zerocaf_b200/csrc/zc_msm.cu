@@ -766,7 +766,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
 
   uint64_t *partial = exchange ? nullptr : out_point_dev;
   if (exchange) {
-    if (!ctx->nccl_comm) return zc_fail(ctx, ZC_ERR_STATE, "zc_msm_sharded_dev needs zc_ctx_set_nccl first");
+    if (!ctx->nccl_comm && !ctx->peers_connected) return zc_fail(ctx, ZC_ERR_STATE, "zc_msm_sharded_dev needs zc_peer_mailbox_connect or zc_ctx_set_nccl first");
     partial = (uint64_t*)ctx->gather_buf + 20 * (size_t)nranks;   // send slot after the nranks receive slots
   }
 
@@ -1019,7 +1019,11 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     }
   }
 
-  if (exchange) {
+  if (exchange && ctx->peers_connected) {
+    // peer stores over NVLink + flag wait + tree fold in one kernel (zc_peer.cu)
+    int32_t rc = zc_peer_exchange_fold(ctx, partial, out_point_dev);
+    if (rc) return rc;
+  } else if (exchange) {
     int32_t rc = zc_nccl_allgather(ctx, partial, ctx->gather_buf, 160);
     if (rc) return rc;
     rc = zc_point_fold_dev(ctx, (const uint64_t*)ctx->gather_buf, (size_t)nranks, out_point_dev);

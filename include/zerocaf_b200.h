@@ -171,13 +171,19 @@ int32_t zc_msm_forget_points(zc_ctx *ctx);
 
 /* Bucket-window-sharded MSM: a collective, every rank calls it with the same (points, scalars, n, window_bits), all
  * resident on its own device.  Rank r accumulates windows w = r (mod nranks), scales its window sums and folds them to
- * one partial point; the partial points are exchanged with ONE ncclAllGather on the context's stream and folded in rank
- * order on every rank, so all ranks return identical bits.  `nccl_comm` is an ncclComm_t created by the caller
+ * one partial point; the partial points are exchanged ONCE -- over NVLink peer memory (zc_peer_mailbox_*) or with one
+ * ncclAllGather on the context's stream -- and folded in a fixed order on every rank, so all ranks return identical bits.  `nccl_comm` is an ncclComm_t created by the caller
  * (e.g. from an ncclUniqueId distributed with torch.distributed); libnccl is resolved at run time with dlopen. */
 int32_t zc_ctx_set_nccl(zc_ctx *ctx, void *nccl_comm, int32_t rank, int32_t nranks);
 int32_t zc_nccl_unique_id(uint8_t id_out[128]);
 int32_t zc_nccl_comm_init(const uint8_t id[128], int32_t rank, int32_t nranks, void **comm_out);
 int32_t zc_nccl_comm_destroy(void *comm);
+/* Exchange over NVLink peer memory instead of NCCL: every rank creates a mailbox in its own HBM (zc_peer_mailbox_create
+ * returns its 64-byte CUDA IPC handle), the handles of all ranks are gathered with the host framework's transport and
+ * passed, in rank order, to zc_peer_mailbox_connect.  zc_msm_sharded_dev then delivers the partial points with peer
+ * stores, waits on flags and folds them in one kernel (a fixed tree of the reference Add: identical bits on all ranks). */
+int32_t zc_peer_mailbox_create(zc_ctx *ctx, uint8_t handle_out[64]);
+int32_t zc_peer_mailbox_connect(zc_ctx *ctx, const uint8_t *handles /* nranks x 64 */, int32_t rank, int32_t nranks);
 int32_t zc_msm_sharded_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev);
 /* the local half only (no exchange): rank r's partial point, for tests of the sharding logic without NCCL */
 int32_t zc_msm_partial_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits,
