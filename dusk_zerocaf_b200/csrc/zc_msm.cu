@@ -703,7 +703,7 @@ __device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
 //   acc = 2^gap_post acc          (gap_post already excludes A0 + a1 + a2 when another group follows)
 // first != 0: acc starts as the identity.  out52 != nullptr: also store the result in the ABI layout.
 // drop0: the first window's comp3 carries weight 1 on every bucket (sub-bucketed short window): A0 - drop0 doublings.
-struct ChainGaps { int pre[8]; };     // doublings before window i of the group (i >= 1), beyond the A0 + a1 + a2 inside it
+struct ChainGaps { int pre[MAX_WINDOWS]; };     // doublings before window i of the group (i >= 1), beyond the A0 + a1 + a2 inside it
 __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ comp, int ng, int first, int a1, int a2, int drop0,
                                                        const ChainGaps gaps, int gap_post, uint32_t* __restrict__ acc_io,
                                                        uint64_t* __restrict__ out52) {
@@ -960,7 +960,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         ZC_CUDA(ctx, cudaStreamWaitEvent(chain, ctx->ev[6 + g], 0));
         const bool last = (g == ngroups - 1);
         ChainGaps gaps;
-        for (int i = 0; i < 8; i++) gaps.pre[i] = 0;
+        for (int i = 0; i < MAX_WINDOWS; i++) gaps.pre[i] = 0;
         for (int i = 1; i < gsz; i++) gaps.pre[i] = c * (tasks[hi - i].w - tasks[hi - 1 - i].w) - A0 - a1 - a2;
         const int gap_post = last ? c * tasks[lo].w : c * (tasks[lo].w - tasks[lo - 1].w) - A0 - a1 - a2;
         msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, drop0, gaps,
