@@ -261,6 +261,7 @@ __device__ __forceinline__ Fe from_mont(const Fe& a) {
 // ============================ products of NORMAL-form operands (no Montgomery) ============================
 // m = 2^K + c with c < 2^125 (4 words = M0..M3), so 2^K = -c (mod m).  For canonical a, b:
 //   T  = (a << SA)(b << SB) = 2^(256-K) a b                     SA + SB = 256 - K       64 wide multiplies
+//        (the shifts are folded into the limb unpacking, fe_load52_shl)
 //   H  = T >> 256 = floor(ab / 2^K),   Lo = (T mod 2^256) >> (256-K) = ab mod 2^K
 //   U  = c H  (< 2^380),   Uh = U >> K (< 2^128),   Ul = U mod 2^K                       32 wide multiplies
 //   V  = c Uh (< 2^253)                                                                   16 wide multiplies
@@ -543,13 +544,6 @@ __device__ __forceinline__ void mul_c_4(uint32_t (&v)[8], const uint32_t (&g)[4]
 // K = bit length of the power of two in m; SA / SB = the two operand pre-shifts
 template <class M> struct Shape { static constexpr int K = 224 + M::TOP, S = 256 - K, SA = S / 2, SB = S - SA; };
 
-template <int S>
-__device__ __forceinline__ void shl_words(uint32_t (&r)[8], const Fe& a) {
-  r[0] = a.w[0] << S;
-#pragma unroll
-  for (int k = 1; k < 8; k++) r[k] = __funnelshift_l(a.w[k - 1], a.w[k], S);
-}
-
 // fold a 16-word product t = 2^S * x (x < m^2, S <= 256 - K) to x mod m, canonical
 template <class M, int S>
 __device__ __forceinline__ Fe fold_product(const uint32_t (&t)[16]) {
@@ -619,24 +613,6 @@ __device__ __forceinline__ Fe fe_sqr_normal_pre(const Fe& a_shl) {
   sqr_wide_8(t, a_shl.w);
   return fold_product<M, 2 * Shape<M>::SA>(t);
 }
-// a * b mod m for canonical NORMAL-form a, b (field.rs:250-262 / scalar.rs:247-258 as a value)
-template <class M>
-__device__ __forceinline__ Fe fe_mul_normal(const Fe& a, const Fe& b) {
-  uint32_t as[8], bs[8], t[16];
-  shl_words<Shape<M>::SA>(as, a);
-  shl_words<Shape<M>::SB>(bs, b);
-  mul_wide_8x8(t, as, bs);
-  return fold_product<M, Shape<M>::S>(t);
-}
-// a^2 mod m (field.rs:302-315 / scalar.rs:272-283 as a value)
-template <class M>
-__device__ __forceinline__ Fe fe_sqr_normal(const Fe& a) {
-  uint32_t as[8], t[16];
-  shl_words<Shape<M>::SA>(as, a);
-  sqr_wide_8(t, as);                       // 2^(2 SA) a^2
-  return fold_product<M, 2 * Shape<M>::SA>(t);
-}
-
 // ---- radix-2^52 limbs (the reference's [u64;5], field.rs:31-32) <-> 8 x u32 --------------------------
 __device__ __forceinline__ Fe fe_from_limbs52(uint64_t l0, uint64_t l1, uint64_t l2, uint64_t l3, uint64_t l4) {
   uint64_t w0 = l0 | (l1 << 52);

@@ -17,7 +17,7 @@ constexpr int TPB = 256;
 enum FeOp { OP_MUL = 0, OP_SQUARE = 1, OP_ADD = 2, OP_SUB = 3, OP_NEG = 4 };
 
 // ---- K1: out[i] = a[i] (op) b[i]   (field.rs:191-315 / scalar.rs:184-283) -------------------------------
-// Normal-form operands: full product + two folds with 2^K = -c (mod m)  (fe_mul_normal, zc_fe.cuh) -- no Montgomery.
+// Normal-form operands: full product + two folds with 2^K = -c (mod m)  (fe_mul_normal_pre, zc_fe.cuh) -- no Montgomery.
 template <class M, int OP>
 __global__ void __launch_bounds__(TPB) fe_op_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
                                                     uint64_t* __restrict__ out, size_t n) {

@@ -5,18 +5,21 @@
 // (/root/reference/src/edwards.rs:102-120, 465-489) as a group element.  Fast formulas are used throughout (cached-operand
 // addition, dedicated doubling), so the result is compared canonically (affine / Ristretto equality), not limb-wise.
 //
-// Pipeline (all on ctx->stream):
-//   prep     points (AoS radix-2^52, normal form) -> cached operands (Y+X, Y-X, Z, 2dT) as 32 x u32.  A normal-form
-//            coordinate vector IS a Montgomery-form representation of the same projective point (all four coordinates
-//            scaled by 1/R), so no conversion multiply is needed -- only the 2d*T product.
-//   digits   scalars -> signed c-bit digits for this rank's windows (+ per-bucket histogram, global atomics)
-//   scan     exclusive scan of the histogram per window (bucket start offsets)
-//   scatter  counting-sort scatter of (point index | sign) into bucket order
-//   accum    one thread per 32-entry segment of the sorted list (balanced), 8M cached additions, prefetched gathers;
-//            fix/heavy stitch buckets that span segments
-//   reduce   sum_k (k+1) * B_k per window: multi-level chunked running sums (chunk m), tree sums per level
-//   combine  Horner over the levels and over this rank's windows with 2^c scalings -> one partial point
-//   exchange (sharded only) ncclAllGather of the partial points + fixed-order fold with the reference Add
+// Pipeline (recorded once into a CUDA graph per argument set; st = the context's stream):
+//   prep     [side stream] points (AoS radix-2^52, normal form) -> cached operands (Y+X, Y-X, Z, 2dT) as 32 x u32.  A
+//            normal-form coordinate vector IS a Montgomery-form representation of the same projective point (all four
+//            coordinates scaled by 1/R), so no conversion multiply is needed -- only the 2d*T product.  Skipped for
+//            prepared points (zc_msm_prepare_points_dev).
+//   digits   [st] scalars -> signed c-bit digits for this rank's windows (+ per-bucket histogram, global atomics)
+//   scan     [st] exclusive scan of the histogram per window (bucket start offsets)
+//   scatter  [st] counting-sort scatter of (point index | sign) into bucket order
+//   then, per group of windows, top-down:
+//   accum    [st] one thread per segment of the sorted list (balanced), 8M cached additions, cp.async-staged operands
+//   fixq / heavy / cube1 / cube2a / cube2b   [one side stream per group] stitch buckets that span segments and reduce
+//            sum_k (k+1) B_k by digit marginals -> four components per window
+//   chain    [chain stream] fold the components into the running sum with Horner doublings, four lanes per operation
+//   exchange (sharded only) partial points over NVLink peer memory fused with the fold (zc_peer.cu), or
+//            ncclAllGather + fold kernel
 #include <stdlib.h>
 #include <vector>
 
@@ -31,8 +34,6 @@ namespace {
 
 constexpr int MAX_WINDOWS = 32;      // ceil(256 / 8)
 constexpr int MAX_GROUPS = 4;        // window groups processed top-down; the scaling chain of one group overlaps the next
-
-struct PtW { uint32_t w[32]; };      // packed point: 4 coordinates x 8 words (extended or cached, Montgomery form)
 
 __device__ __forceinline__ void ld_fe(const uint32_t* __restrict__ p, Fe& a) {
   uint4 lo = *reinterpret_cast<const uint4*>(p);
@@ -50,25 +51,10 @@ __device__ __forceinline__ Pt ld_pt(const uint32_t* __restrict__ p) {
 __device__ __forceinline__ void st_pt(uint32_t* __restrict__ p, const Pt& a) {
   st_fe(p, a.X); st_fe(p + 8, a.Y); st_fe(p + 16, a.Z); st_fe(p + 24, a.T);
 }
-__device__ __forceinline__ PtCached ld_cached(const uint32_t* __restrict__ p) {
-  PtCached r; ld_fe(p, r.YpX); ld_fe(p + 8, r.YmX); ld_fe(p + 16, r.Z); ld_fe(p + 24, r.T2d); return r;
-}
-
 // 1/d * R mod p: recovers 2T from the cached 2dT when a bucket is initialised from its first point
 __device__ __forceinline__ Fe DINV_MONT() {
   return Fe{{0x69c50bb0u, 0xa53327e2u, 0x96b47422u, 0xeaa0ffd5u, 0xfd35fb8fu, 0xd34f1e03u, 0x8d35344bu, 0x0b7245f4u}};
 }
-// the point a cached operand stands for, as (2X, 2Y, 2Z, 2T)
-__device__ __forceinline__ Pt cached_to_pt(const PtCached& c) {
-  typedef ModP M;
-  Pt r;
-  r.X = fe_sub<M>(c.YpX, c.YmX);
-  r.Y = fe_add<M>(c.YpX, c.YmX);
-  r.Z = fe_add<M>(c.Z, c.Z);
-  r.T = mont_mul<M>(c.T2d, DINV_MONT());
-  return r;
-}
-
 // ---- prep ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msm_prep_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
   size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
