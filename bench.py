@@ -348,7 +348,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32x8 Montgomery words (IMAD.WIDE carry chains); ABI u64x5 radix-2^52", "data": "synthetic",
+            "dtype": "u32 (8 x 32-bit words per residue, IMAD.WIDE carry chains); ABI u64x5 radix-2^52", "data": "synthetic",
             "config": {"workload": "config 2: batched 2^24 FieldElement mul+square+reduce per GPU, reference AoS [u64;5] layout in and out",
                        "n_pairs_per_step_per_gpu": n, "e2e_path": "zc_fe_mul_square_batch (host pointers, pinned; chunked H2D / kernel / D2H pipeline inside the library)", "l2_policy": "inputs larger than L2 (1.34 GB read + 1.34 GB written per step)",
                        "parallelism": f"replicated element-wise x{world}, no collective"},

@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restr
 // ---- bucket accumulation, balanced: one thread per SEGMENT of SEG consecutive sorted entries ------------------------
 // A thread walks its SEG entries, summing runs of equal bucket.  A run that covers its whole bucket is stored straight
 // into buckets[]; a run cut by a segment boundary goes to the segment's H slot (run containing the segment's first
-// entry) or T slot (run containing its last entry, when that is a different run).  msm_fix_kernel then stitches the
-// buckets that span several segments.  Every thread does the same number of additions, whatever the digit
+// entry) or T slot (run containing its last entry, when that is a different run).  load_bucket / msm_heavy_kernel then
+// stitch the buckets that span several segments.  Every thread does the same number of additions, whatever the digit
 // distribution (a top window with few, heavy buckets used to serialise thousands of additions in one thread).
 constexpr int SEG_MAX = 32;           // segment length is 8, 16 or 32 (chosen per call from the amount of work)
 constexpr int ACC_TPB = 128;
