@@ -65,6 +65,28 @@ __global__ void __launch_bounds__(256) msm_prep_kernel(const uint64_t* __restric
   st_fe(o, c.YpX); st_fe(o + 8, c.YmX); st_fe(o + 16, c.Z); st_fe(o + 24, c.T2d);
 }
 
+// prepared points: normalise to Z = 1 first (one inversion per point, paid once per point set), so that every later
+// accumulation step is a 7-multiplication mixed addition.  Cached form (y+x, y-x, 1, 2dxy), all in Montgomery form.
+__device__ __noinline__ Fe prep_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
+__global__ void __launch_bounds__(128) msm_prep_affine_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
+  typedef ModP M;
+  size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  Pt p = pt_to_mont(pt_load52(points + 20 * i));
+  // Z^(p-2): p - 2 = 2^252 + (c - 2), plain square-and-multiply over a compile-time exponent
+  const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
+  Fe zi = p.Z;
+#pragma unroll 1
+  for (int bit = 251; bit >= 0; bit--) {
+    zi = prep_mul(zi, zi);
+    if ((e[bit >> 5] >> (bit & 31)) & 1u) zi = prep_mul(zi, p.Z);
+  }
+  const Fe x = prep_mul(p.X, zi), y = prep_mul(p.Y, zi);
+  uint32_t* o = cached + 32 * i;
+  st_fe(o, fe_add<M>(y, x)); st_fe(o + 8, fe_sub<M>(y, x)); st_fe(o + 16, Consts<M>::R1());
+  st_fe(o + 24, prep_mul(prep_mul(x, y), D2_MONT()));
+}
+
 // ---- digits + histogram ----------------------------------------------------------------------------------------
 // digit d_w in [-2^(c-1), 2^(c-1)):  s = sum_w d_w 2^(c w).  Bucket slot = |d| - 1 in [0, 2^(c-1)).
 // Recoding without a carry chain: with H = sum_w 2^(c-1) 2^(c w),  d_w = ((s + H) >> c w) mod 2^c  -  2^(c-1)
@@ -215,6 +237,8 @@ __device__ __forceinline__ Fe lds_fe(const uint4* __restrict__ p) {      // two 
 __device__ __noinline__ Fe acc_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
 
 // p + (+-q) with q staged in shared memory (q points at this thread's piece 0); add-2008-hwcd-3, a = -1
+// AFFINE: the staged operands have Z = 1 (prepared points are normalised once), so D = 2 Z1 needs no product: 7M.
+template <bool AFFINE>
 __device__ __forceinline__ Pt pt_add_staged(const Pt& p, const uint4* __restrict__ q, bool neg) {
   typedef ModP M;
   Fe A = acc_mul(fe_sub<M>(p.Y, p.X), lds_fe(q + (neg ? 0 : 2) * ACC_TPB));
@@ -222,7 +246,7 @@ __device__ __forceinline__ Pt pt_add_staged(const Pt& p, const uint4* __restrict
   Fe t2d = lds_fe(q + 6 * ACC_TPB);
   if (neg) t2d = fe_neg<M>(t2d);
   Fe C = acc_mul(p.T, t2d);
-  Fe D = acc_mul(p.Z, lds_fe(q + 4 * ACC_TPB));
+  Fe D = AFFINE ? p.Z : acc_mul(p.Z, lds_fe(q + 4 * ACC_TPB));
   D = fe_add<M>(D, D);
   Fe E = fe_sub<M>(B, A);
   Fe F = fe_sub<M>(D, C);
@@ -249,6 +273,7 @@ __device__ __forceinline__ Pt staged_to_pt(const uint4* __restrict__ q, bool neg
   return r;
 }
 
+template <bool AFFINE>
 __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
                                                                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
                                                                size_t n_pad, int nseg, int seg, int nwl, int nb,
@@ -313,7 +338,7 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
       run_start = k;
       acc = staged_to_pt(q, neg);
     } else {
-      acc = pt_add_staged(acc, q, neg);
+      acc = pt_add_staged<AFFINE>(acc, q, neg);
     }
     e_cur = e_nxt;
   }
@@ -846,7 +871,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     // prepared points (zc_msm_prepare_points_dev): the cached operands at the head of the workspace are reused
     const bool use_prepared = points && ctx->prep_points == (const void*)points && ctx->prep_n == n;
     if (use_prepared && !ctx->prep_valid) {                    // the workspace was reallocated since: prepare again
-      msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(points, cached, n); ctx->launches++;
+      msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(points, cached, n); ctx->launches++;
       ctx->prep_valid = true;
     }
     uint64_t nlaunch = 0;
@@ -913,7 +938,11 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg_alloc), *g_partT = partT + 32 * ((size_t)lo * nseg_alloc);
         uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
         if (g == 0 && !use_prepared) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
-        msm_accum_kernel<<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT); nlaunch++; mark(st, 0, "msm_accum_kernel");
+        if (use_prepared)
+          msm_accum_kernel<true><<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+        else
+          msm_accum_kernel<false><<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+        nlaunch++; mark(st, 0, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
@@ -1032,7 +1061,7 @@ int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points, size_t n)
     ZC_CUDA(ctx, cudaMalloc(&ctx->msm_ws, need));
     ctx->msm_ws_bytes = need;
   }
-  msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(points, (uint32_t*)ctx->msm_ws, n);
+  msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)ctx->msm_ws, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
   ctx->prep_points = points; ctx->prep_n = n; ctx->prep_valid = true;

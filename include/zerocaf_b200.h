@@ -164,7 +164,8 @@ int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
 
 /* Fixed generators (bulletproofs G_i, H_i): prepare the MSM operands once.  After zc_msm_prepare_points_dev(points, n),
  * zc_msm_dev / zc_msm_partial_dev / zc_msm_sharded_dev calls with the SAME device pointer and n reuse the cached
- * (Y+X, Y-X, Z, 2dT) array kept in the context instead of rebuilding it per call.  The caller must not modify points[]
+ * operand array kept in the context instead of rebuilding it per call; the points are normalised to Z = 1 once (one field
+ * inversion per point), so every bucket addition of the later calls is a 7-multiplication mixed addition instead of 8.  The caller must not modify points[]
  * in place while it is prepared; zc_msm_forget_points drops the cache.  Results are unchanged. */
 int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t n);
 int32_t zc_msm_forget_points(zc_ctx *ctx);
