@@ -12,7 +12,7 @@
 //            prepared points (zc_msm_prepare_points_dev).
 //   digits   [st] scalars -> signed c-bit digits for this rank's windows (+ per-bucket histogram, global atomics)
 //   scan     [st] exclusive scan of the histogram per window (bucket start offsets)
-//   scatter  [st] counting-sort scatter of (point index | sign) into bucket order
+//   scatter  [st] counting-sort scatter of (point index | sign) into bucket order (offset + the rank the histogram atomic returned)
 //   then, per group of windows, top-down:
 //   accum    [st] one thread per segment of the sorted list (balanced), 8M cached additions, cp.async-staged operands
 //   fixq / heavy / cube1 / cube2a / cube2b   [one side stream per group] stitch buckets that span segments and reduce
@@ -108,7 +108,8 @@ struct WinMap { int16_t tl[MAX_WINDOWS]; uint32_t p0[MAX_WINDOWS], p1[MAX_WINDOW
 
 template <int C>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, const WinMap map,
-                                                         int32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+                                                         int32_t* __restrict__ digits, uint32_t* __restrict__ ranks,
+                                                         uint32_t* __restrict__ hist) {
   constexpr int NWIN = (256 + C - 1) / C;
   constexpr uint32_t HALF = 1u << (C - 1), MASK = (1u << C) - 1u, NB = HALF;
   size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restr
         const int SUB = short_window_sub_bits(C, w);      // top window(s) of a 250-bit scalar: few distinct digits
         if (SUB > 0) slot = ((slot << SUB) | ((uint32_t)i & ((1u << SUB) - 1u))) & (NB - 1u);
         key = d < 0 ? -(int32_t)(slot + 1u) : (int32_t)(slot + 1u);
-        atomicAdd(&hist[(size_t)wl * NB + slot], 1u);
+        // the histogram atomic also hands out this entry's rank inside its bucket: the scatter needs no second atomic
+        ranks[(size_t)wl * n + i] = atomicAdd(&hist[(size_t)wl * NB + slot], 1u);
       }
       digits[(size_t)wl * n + i] = key;
     }
@@ -159,8 +161,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restr
 // ---- exclusive scan of each window's histogram (one block of SCAN_TPB threads per local window) -----------------------
 // Thread t owns PER = nb / SCAN_TPB consecutive counters (16-byte loads), warps scan by shuffle, one shared-memory hop.
 constexpr int SCAN_TPB = 1024;
-__global__ void __launch_bounds__(SCAN_TPB) msm_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ offs,
-                                                            uint32_t* __restrict__ cursor, int nb) {
+__global__ void __launch_bounds__(SCAN_TPB) msm_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ offs, int nb) {
   __shared__ uint32_t wtot[32];
   const int wl = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const uint32_t* h = hist + (size_t)wl * nb;
@@ -185,20 +186,20 @@ __global__ void __launch_bounds__(SCAN_TPB) msm_scan_kernel(const uint32_t* __re
     uint4 q = *reinterpret_cast<const uint4*>(h + lo + k);
     uint4 o; o.x = run; o.y = run + q.x; o.z = o.y + q.y; o.w = o.z + q.z; run = o.w + q.w;
     *reinterpret_cast<uint4*>(offs + (size_t)wl * nb + lo + k) = o;
-    *reinterpret_cast<uint4*>(cursor + (size_t)wl * nb + lo + k) = o;
   }
 }
 
 // ---- scatter: counting sort of point indices into bucket order ----------------------------------------------------
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restrict__ digits, size_t n, size_t n_pad, int nwl, int nb,
-                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restrict__ digits, const uint32_t* __restrict__ ranks,
+                                                          size_t n, size_t n_pad, int nwl, int nb,
+                                                          const uint32_t* __restrict__ offs, uint32_t* __restrict__ sorted) {
   size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= n * (size_t)nwl) return;
   size_t wl = g / n, i = g - wl * n;
   int32_t d = digits[g];
   if (d == 0) return;
   uint32_t slot = (uint32_t)(d < 0 ? -d : d) - 1u;
-  uint32_t pos = atomicAdd(&cursor[wl * nb + slot], 1u);
+  const uint32_t pos = offs[wl * nb + slot] + ranks[g];
   sorted[wl * n_pad + pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
 }
 
@@ -803,7 +804,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o_heavy = o; o = align_up(o + 256 * MAX_GROUPS + (size_t)nwl * nb * 4, 256);
     size_t o_hist = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
     size_t o_offs = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
-    size_t o_cursor = o; o = align_up(o + (size_t)nwl * nb * 4, 256);
+    size_t o_ranks = o;  o = align_up(o + (size_t)nwl * n * 4, 256);
     size_t o_buckets = o; o = align_up(o + (size_t)nwl * nb * 128, 256);
     const int bits = c - 1;                                     // nb = 2^bits, bits in 7..15
     const int a1 = 2;                                           // warps per cube block = 2^a1 (bits >= 7)
@@ -835,7 +836,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     uint32_t *heavy_count = (uint32_t*)(ws + o_heavy);          // one counter per group, 256 B apart
     uint32_t *heavy_list = heavy_count + 64 * MAX_GROUPS;
     uint32_t *offs = (uint32_t*)(ws + o_offs);
-    uint32_t *cursor = (uint32_t*)(ws + o_cursor);
+    uint32_t *ranks = (uint32_t*)(ws + o_ranks);
     uint32_t *buckets = (uint32_t*)(ws + o_buckets);
     uint32_t *btot = (uint32_t*)(ws + o_tot);
     uint32_t *pm1 = (uint32_t*)(ws + o_pm1);
@@ -907,17 +908,17 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       {
         const unsigned grid = (unsigned)((n + 255) / 256);
         switch (c) {
-#define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, wmap, digits, hist); break;
+#define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, wmap, digits, ranks, hist); break;
           ZC_DIGITS_CASE(8) ZC_DIGITS_CASE(9) ZC_DIGITS_CASE(10) ZC_DIGITS_CASE(11) ZC_DIGITS_CASE(12)
           ZC_DIGITS_CASE(13) ZC_DIGITS_CASE(14) ZC_DIGITS_CASE(15) ZC_DIGITS_CASE(16)
 #undef ZC_DIGITS_CASE
         }
         nlaunch++; mark(st, 0, "msm_digits_kernel");
       }
-      msm_scan_kernel<<<nwl, SCAN_TPB, 0, st>>>(hist, offs, cursor, nb); nlaunch++; mark(st, 0, "msm_scan_kernel");
+      msm_scan_kernel<<<nwl, SCAN_TPB, 0, st>>>(hist, offs, nb); nlaunch++; mark(st, 0, "msm_scan_kernel");
       {
         size_t tot = n * (size_t)nwl;
-        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, n, n_pad, nwl, nb, cursor, sorted); nlaunch++; mark(st, 0, "msm_scatter_kernel");
+        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, ranks, n, n_pad, nwl, nb, offs, sorted); nlaunch++; mark(st, 0, "msm_scatter_kernel");
       }
       // Task groups, top-down (local index wl ascends with the window index).  After a group's buckets are
       // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
