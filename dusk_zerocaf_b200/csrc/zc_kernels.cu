@@ -190,6 +190,31 @@ __global__ void __launch_bounds__(STRICT_TPB) scalar_mul_strict_kernel(const uin
 // registers only (4 blocks of 128 threads per SM instead of 3 blocks of 64), which is what the dependent multiply chains
 // need to keep the integer pipe busy.
 constexpr int SM_FAST_TPB = 128;
+// One out-of-line multiplier keeps the window loop (a doubling and an addition, 16 products) at a few KB of code instead
+// of ~60 KB of inlined carry chains: with 16 warps per SM spread over the loop, instruction fetch was a visible stall.
+__device__ __noinline__ Fe smf_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
+__device__ __forceinline__ Pt smf_double(const Pt& p) {           // pt_double_fast (dbl-2008-hwcd, a = -1)
+  typedef ModP M;
+  Fe A = smf_mul(p.X, p.X), B = smf_mul(p.Y, p.Y), Z2 = smf_mul(p.Z, p.Z);
+  Fe C = fe_add<M>(Z2, Z2);
+  Fe D = fe_neg<M>(A);
+  Fe S = fe_add<M>(p.X, p.Y);
+  Fe E = fe_sub<M>(fe_sub<M>(smf_mul(S, S), A), B);
+  Fe G = fe_add<M>(D, B);
+  Fe F = fe_sub<M>(G, C);
+  Fe H = fe_sub<M>(D, B);
+  return Pt{smf_mul(E, F), smf_mul(G, H), smf_mul(F, G), smf_mul(E, H)};
+}
+__device__ __forceinline__ Pt smf_add(const Pt& p, const PtCached& q) {   // pt_add_cached (add-2008-hwcd-3)
+  typedef ModP M;
+  Fe A = smf_mul(fe_sub<M>(p.Y, p.X), q.YmX);
+  Fe B = smf_mul(fe_add<M>(p.Y, p.X), q.YpX);
+  Fe C = smf_mul(p.T, q.T2d);
+  Fe D = smf_mul(p.Z, q.Z);
+  D = fe_add<M>(D, D);
+  Fe E = fe_sub<M>(B, A), F = fe_sub<M>(D, C), G = fe_add<M>(D, C), H = fe_add<M>(B, A);
+  return Pt{smf_mul(E, F), smf_mul(G, H), smf_mul(F, G), smf_mul(E, H)};
+}
 __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const uint64_t* __restrict__ points,
                                                                          const uint64_t* __restrict__ scalars,
                                                                          uint64_t* __restrict__ out, size_t n,
@@ -225,7 +250,7 @@ __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const u
       Pt acc = P;
 #pragma unroll 1
       for (int e = 1; e < 8; e++) {
-        acc = pt_add_cached(acc, c1);
+        acc = smf_add(acc, c1);
         store_entry(e, pt_to_cached(acc));
       }
     }
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const u
     for (int j = 63; j >= 0; j--) {
       if (j != 63) {
 #pragma unroll 1
-        for (int r = 0; r < 4; r++) Q = pt_double_fast(Q);
+        for (int r = 0; r < 4; r++) Q = smf_double(Q);
       }
       uint32_t nib = 0;
 #pragma unroll
@@ -262,7 +287,7 @@ __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const u
       if (__any_sync(0xffffffffu, mag != 0)) {
         PtCached c = load_entry(mag ? mag - 1 : 0);
         if (d < 0) c = pt_cached_neg(c);
-        Pt r = pt_add_cached(Q, c);
+        Pt r = smf_add(Q, c);
         if (mag != 0) Q = r;
       }
     }
