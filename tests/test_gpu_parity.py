@@ -429,6 +429,45 @@ def test_msm_sharding_partials_fold_to_full(zc, oracle):
 # ---------------------------------------------------------------------------------------------------------
 # host-side mirror types read like the reference's own tests
 # ---------------------------------------------------------------------------------------------------------
+def test_msm_call_sequence_reuses_workspace_and_graph(zc, oracle):
+    """Back-to-back MSMs with changing sizes, windows, shard parameters and repeated identical calls: the grow-only
+    workspace, the cached CUDA graph (replayed when the arguments repeat, re-recorded when they change) and the sharded
+    partials must never leak state from one call into the next."""
+    import torch
+    ctx = zc.default_context()
+    L = ctx._L
+    nmax = 6000
+    P = synth_points(oracle, 90, nmax)
+    s = oracle.synth_scalar(SEED, 91, 0, nmax)
+    dP = torch.from_numpy(P.view(np.int64)).cuda()
+    dS = torch.from_numpy(s.view(np.int64)).cuda()
+    out = torch.zeros(20, dtype=torch.int64, device="cuda")
+    want = {}
+    seq = [(6000, 16, 0, 1), (6000, 16, 0, 1), (777, 9, 0, 1), (6000, 16, 0, 1), (1, 16, 0, 1), (2049, 13, 1, 2),
+           (2049, 13, 1, 2), (2049, 13, 0, 2), (6000, 8, 0, 1), (33, 16, 3, 4), (6000, 16, 0, 1)]
+    for n, c, r, R in seq:
+        ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, r, R, out.data_ptr()))
+        ctx.sync()
+        got = out.cpu().numpy().view(np.uint64).copy()
+        assert oracle.pt_is_valid(got), (n, c, r, R)
+        if R == 1:
+            if n not in want:
+                want[n] = oracle.msm_naive(P[:n], s[:n], threads=8)
+            assert oracle.pt_eq(got, want[n]), (n, c)
+        else:                                                  # fold all ranks' partials for this (n, c, R)
+            parts = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
+            for rr in range(R):
+                ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, rr, R, parts[rr].data_ptr()))
+            ctx.sync()
+            assert torch.equal(parts[r], out) or oracle.pt_eq(parts[r].cpu().numpy().view(np.uint64), got)
+            tot = torch.zeros(20, dtype=torch.int64, device="cuda")
+            ctx.check(L.zc_point_fold_dev(ctx._h, parts.data_ptr(), R, tot.data_ptr()))
+            ctx.sync()
+            if n not in want:
+                want[n] = oracle.msm_naive(P[:n], s[:n], threads=8)
+            assert oracle.pt_eq(tot.cpu().numpy().view(np.uint64), want[n]), (n, c, R)
+
+
 def test_msm_prepared_points(zc, oracle):
     """zc_msm_prepare_points_dev: same result with the cached operands, for several scalar vectors, window sizes (the
     workspace grows -> the cache is rebuilt) and after forgetting."""
