@@ -871,7 +871,8 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     // latency-bound sequence -- at 8 ranks the per-rank kernels are short enough for launch gaps to rival the math.
     // prepared points (zc_msm_prepare_points_dev): the cached operands at the head of the workspace are reused
     const bool use_prepared = points && ctx->prep_points == (const void*)points && ctx->prep_n == n;
-    if (use_prepared && !ctx->prep_valid) {                    // the workspace was reallocated since: prepare again
+    if (!use_prepared) ctx->prep_valid = false;                // this call's operand pass overwrites the cached array
+    if (use_prepared && !ctx->prep_valid) {                    // the workspace was reallocated / reused since: prepare again
       msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(points, cached, n); ctx->launches++;
       ctx->prep_valid = true;
     }

@@ -485,6 +485,16 @@ def test_msm_prepared_points(zc, oracle):
         ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, out.data_ptr()))
         ctx.sync()
         assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8)), (k, c)
+    # an MSM over OTHER points in between reuses the workspace: the prepared set must be rebuilt, not trusted
+    P2 = synth_points(oracle, 85, 700)
+    s2 = oracle.synth_scalar(SEED, 86, 0, 700)
+    dP2, dS2 = torch.from_numpy(P2.view(np.int64)).cuda(), torch.from_numpy(s2.view(np.int64)).cuda()
+    ctx.check(L.zc_msm_dev(ctx._h, dP2.data_ptr(), dS2.data_ptr(), 700, 16, out.data_ptr()))
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P2, s2, threads=8))
+    ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
     ctx.check(L.zc_msm_forget_points(ctx._h))
     ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
     ctx.sync()
