@@ -313,6 +313,7 @@ int32_t zc_point_to_affine_batch(zc_ctx* ctx, const uint64_t* p, uint64_t* out_x
 
 int32_t zc_ristretto_compress_batch_dev(zc_ctx* ctx, const uint64_t* p, uint8_t* out_bytes, size_t n) {
   ZC_ENC_PROLOGUE(ctx, n, p && out_bytes);
+  if ((uintptr_t)out_bytes & 15u) return zc_fail(ctx, ZC_ERR_SIZE, "out_bytes must be 16-byte aligned");
   ristretto_compress_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(p, out_bytes, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
