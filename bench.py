@@ -123,6 +123,34 @@ def cpu_field_rate(n_sample, threads, repeats=1):
     return 2.0 * n_sample / best, best
 
 
+def cpu_secondary_rates(threads):
+    """Reference-equivalent CPU rates for configs 3-5 on bounded samples: point adds (2^16), strict
+    scalar-muls (2^10), and the naive MSM the reference would run (sum of double_and_add, 2^10 points)."""
+    from oracle import oracle as o
+    from dusk_zerocaf_b200 import synth
+    o.build()
+    n_sm = 1 << 10
+    base = np.tile(synth.BASEPOINT, (n_sm, 1))
+    r = synth.synth_scalar(100, 0, n_sm)
+    t0 = time.perf_counter()
+    P = o.pt_scalar_mul_batch(base, r, threads=threads)
+    t_sm = time.perf_counter() - t0
+    n_add = 1 << 16
+    PP = np.tile(P, (n_add // n_sm, 1))
+    QQ = np.roll(PP, 7, axis=0)
+    t0 = time.perf_counter()
+    o.pt_add_batch(PP, QQ, threads=threads)
+    t_add = time.perf_counter() - t0
+    s = synth.synth_scalar(102, 0, n_sm)
+    t0 = time.perf_counter()
+    o.msm_naive(P, s, threads=threads)
+    t_msm = time.perf_counter() - t0
+    return {"point_adds_per_s": n_add / t_add, "point_add_sample": n_add,
+            "scalar_muls_per_s": n_sm / t_sm, "scalar_mul_sample": n_sm,
+            "msm_2p20_seconds_extrapolated": t_msm * ((1 << 20) / n_sm), "msm_sample_points": n_sm,
+            "note": "oracle port (1:1 restatement of edwards.rs:102-120, 465-489), linear extrapolation for the MSM"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -342,7 +370,7 @@ def run_b200(args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"2^23 of the 2^24 pairs (mul+square), best of 3, {cores} pthreads, oracle/zerocaf_oracle.c "
                          f"(1:1 restatement of field.rs:250-262,302-315; no Rust toolchain here)",
-               "single_thread_value": v1}
+               "single_thread_value": v1, "configs_3_to_5": cpu_secondary_rates(cores)}
 
     if rank == 0:
         line = {
