@@ -87,6 +87,7 @@ def lib():
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
     L.zc_msm_prepare_points_dev.argtypes = [vp, vp, sz]
     L.zc_msm_forget_points.argtypes = [vp]
+    L.zc_msm_prepare_fixed_base_dev.argtypes = [vp, vp, sz, i32, i32, i32]
     L.zc_msm_partial_dev.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
     L.zc_point_fold_dev.argtypes = [vp, vp, sz, vp]
     L.zc_ctx_set_nccl.argtypes = [vp, vp, i32, i32]

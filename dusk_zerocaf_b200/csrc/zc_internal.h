@@ -55,6 +55,13 @@ struct zc_ctx {
   const void *prep_points = nullptr;
   size_t prep_n = 0;
   bool prep_valid = false;
+  // fixed-base MSM tables (zc_msm_prepare_fixed_base_dev): 2^(c w) P_i for this rank's windows, affine cached form
+  void *fb_table = nullptr;
+  void *fb_corr = nullptr;          // [u64;20]: minus the constant a spread short window adds (zc_msm.cu), or null
+  size_t fb_table_bytes = 0;
+  const void *fb_points = nullptr;
+  size_t fb_n = 0;
+  int32_t fb_c = 0, fb_rank = 0, fb_nranks = 0;
   void *basepoint_table = nullptr;  // fixed-base table (zc_fixed.cu), built on first use
   void *msm_graph_exec = nullptr;   // cudaGraphExec_t of the last MSM configuration
   zc_msm_key msm_key = {};

@@ -432,6 +432,8 @@ int32_t zc_ctx_destroy(zc_ctx* ctx) {
   for (int i = 0; i < 6; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->msm_ws) cudaFree(ctx->msm_ws);
   if (ctx->basepoint_table) cudaFree(ctx->basepoint_table);
+  if (ctx->fb_table) cudaFree(ctx->fb_table);
+  if (ctx->fb_corr) cudaFree(ctx->fb_corr);
   if (ctx->gather_buf) cudaFree(ctx->gather_buf);
   if (ctx->peers_connected) for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && ctx->peers.p[r]) cudaIpcCloseMemHandle(ctx->peers.p[r]);
   if (ctx->mailbox) cudaFree(ctx->mailbox);

@@ -102,9 +102,66 @@ __host__ __device__ constexpr int short_window_sub_bits(int c, int w) {
   return ba < c - 1 ? (c - 1) - ba : 0;
 }
 
+// Fixed-base (merged) mode has one bucket set for all windows, so a short window cannot get sub-buckets of its own.  It is
+// spread differently: its table rows are scaled by 2^(c w - SM) instead of 2^(c w) and its (non-negative) digit becomes
+// d' = d 2^SM + (i mod 2^SM), which lands anywhere in the bucket range.  The extra  sum_i (i mod 2^SM) 2^(c w - SM) P_i  does
+// not depend on the scalars: it is computed once with the tables and subtracted by the chain kernel.  SM = SUB - 1 keeps
+// d' <= 2^(c-2) + 2^SM inside the bucket range for every digit a canonical scalar can produce.
+__host__ __device__ constexpr int merged_spread_bits(int c, int w) {
+  return (250 - c * w > 0 && short_window_sub_bits(c, w) > 1) ? short_window_sub_bits(c, w) - 1 : 0;
+}
+
 // Which of this rank's tasks (local index tl, or -1) takes window w, and for which point range [p0, p1).  A task is a
 // window (all points) today; the range exists so that a window can be split by points between ranks.
-struct WinMap { int16_t tl[MAX_WINDOWS]; uint32_t p0[MAX_WINDOWS], p1[MAX_WINDOWS]; };
+// merged != 0 (fixed-base tables): all of the rank's windows share ONE set of buckets -- the table entry of (window, point)
+// is already scaled by 2^(c w), so only the digit's magnitude picks the bucket.
+struct WinMap { int16_t tl[MAX_WINDOWS]; uint32_t p0[MAX_WINDOWS], p1[MAX_WINDOWS]; int32_t merged; };
+
+// fixed-base tables: row (t, i) = 2^(c w_t) P_i in the same affine cached form, for the windows w_0 < w_1 < ... this rank
+// owns.  One thread per point walks up the windows with dedicated doublings and normalises at every owned window (one
+// inversion each): a one-time cost per generator set, after which an MSM needs neither per-window buckets nor any doubling.
+struct FbWindows { int nwl; int16_t w[MAX_WINDOWS]; };      // a spread short window's rows are 2^(c w - SM) P_i (merged_spread_bits)
+__device__ __noinline__ Pt prep_double(Pt p) { return pt_double_fast(p); }
+__global__ void __launch_bounds__(128) msm_fixed_base_table_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ table,
+                                                                   size_t n, int c, const FbWindows win) {
+  typedef ModP M;
+  size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  Pt p = pt_to_mont(pt_load52(points + 20 * i));
+  const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
+  int at = 0;                                    // p = 2^at P_i
+#pragma unroll 1
+  for (int t = 0; t < win.nwl; t++) {
+    const int target = c * (int)win.w[t] - merged_spread_bits(c, (int)win.w[t]);
+#pragma unroll 1
+    for (int j = at; j < target; j++) p = prep_double(p);
+    at = target;
+    Fe zi = p.Z;
+#pragma unroll 1
+    for (int bit = 251; bit >= 0; bit--) {
+      zi = prep_mul(zi, zi);
+      if ((e[bit >> 5] >> (bit & 31)) & 1u) zi = prep_mul(zi, p.Z);
+    }
+    const Fe x = prep_mul(p.X, zi), y = prep_mul(p.Y, zi);
+    uint32_t* o = table + 32 * ((size_t)t * n + i);
+    st_fe(o, fe_add<M>(y, x)); st_fe(o + 8, fe_sub<M>(y, x)); st_fe(o + 16, Consts<M>::R1());
+    st_fe(o + 24, prep_mul(prep_mul(x, y), D2_MONT()));
+  }
+}
+
+// scalars of the spread correction  K = sum_i (i mod 2^sm) 2^shift P_i  (radix-2^52 limbs)
+__global__ void __launch_bounds__(256) msm_spread_scalars_kernel(uint64_t* __restrict__ scalars, size_t n, int sm, int shift) {
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t r = (uint64_t)i & ((1ull << sm) - 1ull);
+  const int limb = shift / 52, bit = shift % 52;
+  uint64_t out[5] = {0, 0, 0, 0, 0};
+  out[limb] = (r << bit) & ((1ull << 52) - 1ull);
+  if (limb + 1 < 5) out[limb + 1] = bit ? (r >> (52 - bit)) : 0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) scalars[5 * i + k] = out[k];
+}
+
 
 template <int C>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, const WinMap map,
@@ -148,10 +205,22 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restr
       if (d != 0 && i >= map.p0[w] && i < map.p1[w]) {
         uint32_t slot = (uint32_t)(d < 0 ? -d : d) - 1u;
         const int SUB = short_window_sub_bits(C, w);      // top window(s) of a 250-bit scalar: few distinct digits
-        if (SUB > 0) slot = ((slot << SUB) | ((uint32_t)i & ((1u << SUB) - 1u))) & (NB - 1u);
+        if (SUB > 0 && !map.merged) slot = ((slot << SUB) | ((uint32_t)i & ((1u << SUB) - 1u))) & (NB - 1u);
         key = d < 0 ? -(int32_t)(slot + 1u) : (int32_t)(slot + 1u);
+      }
+      const int SM = merged_spread_bits(C, w);
+      if (SM > 0 && map.merged && i >= map.p0[w] && i < map.p1[w]) {
+        const int32_t dd = d * (1 << SM) + (int32_t)((uint32_t)i & ((1u << SM) - 1u));
+        key = 0;
+        if (dd != 0) {
+          const uint32_t slot = ((uint32_t)(dd < 0 ? -dd : dd) - 1u) & (NB - 1u);
+          key = dd < 0 ? -(int32_t)(slot + 1u) : (int32_t)(slot + 1u);
+        }
+      }
+      if (key != 0) {
+        const uint32_t slot = (uint32_t)(key < 0 ? -key : key) - 1u;
         // the histogram atomic also hands out this entry's rank inside its bucket: the scatter needs no second atomic
-        ranks[(size_t)wl * n + i] = atomicAdd(&hist[(size_t)wl * NB + slot], 1u);
+        ranks[(size_t)wl * n + i] = atomicAdd(&hist[(map.merged ? (size_t)0 : (size_t)wl * NB) + slot], 1u);
       }
       digits[(size_t)wl * n + i] = key;
     }
@@ -191,7 +260,7 @@ __global__ void __launch_bounds__(SCAN_TPB) msm_scan_kernel(const uint32_t* __re
 
 // ---- scatter: counting sort of point indices into bucket order ----------------------------------------------------
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restrict__ digits, const uint32_t* __restrict__ ranks,
-                                                          size_t n, size_t n_pad, int nwl, int nb,
+                                                          size_t n, size_t n_pad, int nwl, int nb, int merged,
                                                           const uint32_t* __restrict__ offs, uint32_t* __restrict__ sorted) {
   size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= n * (size_t)nwl) return;
@@ -199,8 +268,13 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restr
   int32_t d = digits[g];
   if (d == 0) return;
   uint32_t slot = (uint32_t)(d < 0 ? -d : d) - 1u;
+  const uint32_t sign = d < 0 ? 0x80000000u : 0u;
+  if (merged) {                                  // one bucket set; the entry names the table row  wl * n + i
+    sorted[offs[slot] + ranks[g]] = (uint32_t)g | sign;
+    return;
+  }
   const uint32_t pos = offs[wl * nb + slot] + ranks[g];
-  sorted[wl * n_pad + pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+  sorted[wl * n_pad + pos] = (uint32_t)i | sign;
 }
 
 // ---- bucket accumulation, balanced: one thread per SEGMENT of SEG consecutive sorted entries ------------------------
@@ -356,16 +430,16 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
 // Buckets with at most FIX_INLINE partials are stitched on the fly by whoever reads them (load_bucket, used by the
 // first reduction stage); heavier ones are queued here for msm_heavy_kernel (one warp per bucket, tree sum), which
 // writes them into buckets[].
-constexpr int FIX_INLINE = 6;
+constexpr int FIX_INLINE = 6;       // per-window buckets; the merged buckets of the fixed-base path choose theirs per call
 __global__ void __launch_bounds__(256) msm_fixq_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                       int seg, int nwl, int nb, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+                                                       int seg, int nwl, int nb, int fix_inline, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
   size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= (size_t)nwl * nb) return;
   const uint32_t cnt = hist[g];
   if (cnt == 0) return;
   const uint32_t o = offs[g], e = o + cnt;
   const uint32_t s_first = o / (uint32_t)seg, s_last = (e - 1) / (uint32_t)seg;
-  if (s_last - s_first + 1 > FIX_INLINE) {
+  if (s_last - s_first + 1 > (uint32_t)fix_inline) {
     uint32_t slot = atomicAdd(heavy_count, 1u);
     heavy_list[slot] = (uint32_t)g;
   }
@@ -379,7 +453,7 @@ __device__ __noinline__ Pt pt_double_ni(Pt p) { return pt_double_fast(p); }
 
 struct BucketSrc {                  // where a group's buckets live (all pointers relative to the group's first window)
   const uint32_t *offs, *hist, *partH, *partT, *buckets;
-  int nseg, nb, seg;
+  int nseg, nb, seg, fix_inline;
 };
 // bucket g of the group, stitched from its segment partials when it spans a few segments
 __device__ __forceinline__ Pt load_bucket(const BucketSrc& b, size_t g) {
@@ -388,7 +462,7 @@ __device__ __forceinline__ Pt load_bucket(const BucketSrc& b, size_t g) {
   if (cnt == 0) return pt_identity_mont();
   const uint32_t o = b.offs[g], e = o + cnt;
   const uint32_t s_first = o / (uint32_t)seg, s_last = (e - 1) / (uint32_t)seg;
-  if (s_first == s_last || s_last - s_first + 1 > FIX_INLINE) return ld_pt(b.buckets + 32 * g);
+  if (s_first == s_last || s_last - s_first + 1 > (uint32_t)b.fix_inline) return ld_pt(b.buckets + 32 * g);
   const size_t wl = g / b.nb;
   const uint32_t* H = b.partH + 32 * (wl * b.nseg);
   const uint32_t* T = b.partT + 32 * (wl * b.nseg);
@@ -718,7 +792,7 @@ __device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
 struct ChainGaps { int pre[MAX_WINDOWS]; };     // doublings before window i of the group (i >= 1), beyond the A0 + a1 + a2 inside it
 __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restrict__ comp, int ng, int first, int a1, int a2, int drop0,
                                                        const ChainGaps gaps, int gap_post, uint32_t* __restrict__ acc_io,
-                                                       uint64_t* __restrict__ out52) {
+                                                       uint64_t* __restrict__ out52, const uint64_t* __restrict__ corr52) {
   const int lane = threadIdx.x;
   const int q = lane & 3, qbase = lane & ~3;
   Pt a0 = first ? pt_identity_mont() : ld_pt(acc_io);
@@ -736,6 +810,8 @@ __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restric
   }
 #pragma unroll 1
   for (int j = 0; j < gap_post; j++) c = quad_double(c, q, qbase);
+  // fixed-base spread correction (ABI layout): normal-form words are a Montgomery-form representative of the same point
+  if (corr52) c = quad_add(c, pt_load52(corr52), q, qbase);
   Pt r;
   r.X = shfl_fe(c, 0); r.Y = shfl_fe(c, 1); r.Z = shfl_fe(c, 2); r.T = shfl_fe(c, 3);
   if (lane == 0) {
@@ -775,6 +851,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
   WinMap wmap;
   for (int w = 0; w < MAX_WINDOWS; w++) { wmap.tl[w] = -1; wmap.p0[w] = 0; wmap.p1[w] = 0; }
   for (int t = 0; t < nwl; t++) { wmap.tl[tasks[t].w] = (int16_t)t; wmap.p0[tasks[t].w] = tasks[t].p0; wmap.p1[tasks[t].w] = tasks[t].p1; }
+  wmap.merged = 0;
 
   uint64_t *partial = exchange ? nullptr : out_point_dev;
   if (exchange) {
@@ -787,25 +864,33 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     int32_t rc = zc_point_fold_dev(ctx, nullptr, 0, partial);
     if (rc) return rc;
   } else {
+    // fixed-base tables prepared for exactly this call shape (zc_msm_prepare_fixed_base_dev): every (window, point) entry is
+    // a row of the table, all of the rank's windows share one bucket set, and there is no doubling chain
+    const bool use_fb = points && ctx->fb_table && ctx->fb_points == (const void*)points && ctx->fb_n == n && ctx->fb_c == c &&
+                        ctx->fb_rank == rank && ctx->fb_nranks == nranks;
+    const int nwb = use_fb ? 1 : nwl;                           // bucket sets
+    wmap.merged = use_fb ? 1 : 0;
+    const size_t fb_entries = (size_t)nwl * n;
+    const int fb_seg = fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8);
     // workspace layout
     size_t o = 0;
-    size_t o_cached = o; o = align_up(o + n * 128, 256);
+    size_t o_cached = o; o = align_up(o + (use_fb ? 0 : n * 128), 256);
     size_t o_digits = o; o = align_up(o + (size_t)nwl * n * 4, 256);
     // Segment length, per task group: 32 when the group holds >= 2^22 entries, 16 below that, 8 for <= 2^19 -- less work
     // gets shorter segments so that the accumulation still fills the GPU (one window of 2^20 points in 32-entry segments
     // is 256 CTAs of 32 serial additions each: latency-bound at 190 us).  Shorter segments mean more partials to stitch
     // per bucket (a 64-entry bucket spans 8-9 segments of 8 and would go to the one-warp-per-bucket heavy path), hence
     // not always 8.  The partial-slot arrays are laid out for the shortest segment.
-    const size_t n_pad = align_up(n, SEG_MAX);
-    const int nseg_alloc = (int)(n_pad / 8);
-    size_t o_sorted = o; o = align_up(o + (size_t)nwl * n_pad * 4 + 256, 256);
-    size_t o_partH = o; o = align_up(o + (size_t)nwl * nseg_alloc * 128, 256);
-    size_t o_partT = o; o = align_up(o + (size_t)nwl * nseg_alloc * 128, 256);
-    size_t o_heavy = o; o = align_up(o + 256 * MAX_GROUPS + (size_t)nwl * nb * 4, 256);
-    size_t o_hist = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
-    size_t o_offs = o;   o = align_up(o + (size_t)nwl * nb * 4, 256);
+    const size_t n_pad = align_up(use_fb ? fb_entries : n, SEG_MAX);
+    const int nseg_alloc = (int)(n_pad / (use_fb ? fb_seg : 8));
+    size_t o_sorted = o; o = align_up(o + (size_t)nwb * n_pad * 4 + 256, 256);
+    size_t o_partH = o; o = align_up(o + (size_t)nwb * nseg_alloc * 128, 256);
+    size_t o_partT = o; o = align_up(o + (size_t)nwb * nseg_alloc * 128, 256);
+    size_t o_heavy = o; o = align_up(o + 256 * MAX_GROUPS + (size_t)nwb * nb * 4, 256);
+    size_t o_hist = o;   o = align_up(o + (size_t)nwb * nb * 4, 256);
+    size_t o_offs = o;   o = align_up(o + (size_t)nwb * nb * 4, 256);
     size_t o_ranks = o;  o = align_up(o + (size_t)nwl * n * 4, 256);
-    size_t o_buckets = o; o = align_up(o + (size_t)nwl * nb * 128, 256);
+    size_t o_buckets = o; o = align_up(o + (size_t)nwb * nb * 128, 256);
     const int bits = c - 1;                                     // nb = 2^bits, bits in 7..15
     const int a1 = 2;                                           // warps per cube block = 2^a1 (bits >= 7)
     const int ab = bits - A0 - a1;                              // block-index bits, split into k2 (a2) and k3 (a3)
@@ -813,13 +898,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     const int nblk = 1 << ab;                                   // cube blocks per window
     const int nw1 = 1 << a1;
     const int ntask = nw1 + 32 + (1 << a2) + (1 << a3);
-    size_t o_tot = o;  o = align_up(o + (size_t)nwl * nblk * 128, 256);
-    size_t o_pm1 = o;  o = align_up(o + (size_t)nwl * nblk * nw1 * 128, 256);
-    size_t o_pm0 = o;  o = align_up(o + (size_t)nwl * nblk * 32 * 128, 256);
-    size_t o_marg = o; o = align_up(o + (size_t)nwl * ntask * 128, 256);
+    size_t o_tot = o;  o = align_up(o + (size_t)nwb * nblk * 128, 256);
+    size_t o_pm1 = o;  o = align_up(o + (size_t)nwb * nblk * nw1 * 128, 256);
+    size_t o_pm0 = o;  o = align_up(o + (size_t)nwb * nblk * 32 * 128, 256);
+    size_t o_marg = o; o = align_up(o + (size_t)nwb * ntask * 128, 256);
     size_t o_fold = o; o = align_up(o + (size_t)4 * nb * 128, 256);      // one per side stream
     size_t o_acc = o;  o = align_up(o + 128, 256);
-    size_t o_comp = o; o = align_up(o + (size_t)nwl * 4 * 128, 256);
+    size_t o_comp = o; o = align_up(o + (size_t)nwb * 4 * 128, 256);
     if (o > ctx->msm_ws_bytes) {
       if (ctx->msm_ws) ZC_CUDA(ctx, cudaFree(ctx->msm_ws));
       ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0; ctx->prep_valid = false;
@@ -870,7 +955,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     // the call's arguments stay the same (repeated proofs over resident generators): one launch instead of a launch-
     // latency-bound sequence -- at 8 ranks the per-rank kernels are short enough for launch gaps to rival the math.
     // prepared points (zc_msm_prepare_points_dev): the cached operands at the head of the workspace are reused
-    const bool use_prepared = points && ctx->prep_points == (const void*)points && ctx->prep_n == n;
+    const bool use_prepared = !use_fb && points && ctx->prep_points == (const void*)points && ctx->prep_n == n;
     if (!use_prepared) ctx->prep_valid = false;                // this call's operand pass overwrites the cached array
     if (use_prepared && !ctx->prep_valid) {                    // the workspace was reallocated / reused since: prepare again
       msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(points, cached, n); ctx->launches++;
@@ -898,9 +983,9 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     };
     auto enqueue = [&]() -> int32_t {
       mark(st, 0, "start");
-      ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwl * nb * 4, st));
+      ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwb * nb * 4, st));
       ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
-      if (!use_prepared) {
+      if (!use_prepared && !use_fb) {
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
         ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[0], 0));
         msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++; mark(side, 1, "msm_prep_kernel");
@@ -916,10 +1001,31 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         }
         nlaunch++; mark(st, 0, "msm_digits_kernel");
       }
-      msm_scan_kernel<<<nwl, SCAN_TPB, 0, st>>>(hist, offs, nb); nlaunch++; mark(st, 0, "msm_scan_kernel");
+      msm_scan_kernel<<<nwb, SCAN_TPB, 0, st>>>(hist, offs, nb); nlaunch++; mark(st, 0, "msm_scan_kernel");
       {
         size_t tot = n * (size_t)nwl;
-        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, ranks, n, n_pad, nwl, nb, offs, sorted); nlaunch++; mark(st, 0, "msm_scatter_kernel");
+        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, ranks, n, n_pad, nwl, nb, use_fb ? 1 : 0, offs, sorted); nlaunch++; mark(st, 0, "msm_scatter_kernel");
+      }
+      if (use_fb) {
+        // one bucket set over all (window, point) entries: accumulate, stitch, reduce, combine the four cube components
+        // (A0 + a1 + a2 doublings in all).  A typical bucket spans entries / (nb seg) segments; up to twice that is stitched
+        // inline by the reduction's loads, the few heavier ones (buckets the short top window also feeds) one warp each.
+        const int seg = fb_seg, nseg = (int)(n_pad / seg);
+        const int fix_inline = 2 * (int)(fb_entries / ((size_t)nb * seg)) + FIX_INLINE;
+        msm_accum_kernel<true><<<(unsigned)((nseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>((const uint32_t*)ctx->fb_table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
+        nlaunch++; mark(st, 0, "msm_accum_kernel");
+        msm_fixq_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(offs, hist, seg, 1, nb, fix_inline, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_fixq_kernel");
+        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_heavy_kernel");
+        const BucketSrc src = {offs, hist, partH, partT, buckets, nseg, nb, seg, fix_inline};
+        const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
+        msm_cube1_kernel<<<(unsigned)nblk, 32 * nw1, cube_smem, st>>>(src, 0u, a1, btot, pm1, pm0); nlaunch++; mark(st, 0, "msm_cube1_kernel");
+        msm_cube2a_kernel<<<(unsigned)((ntask + 3) / 4), 128, 0, st>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(st, 0, "msm_cube2a_kernel");
+        msm_cube2b_kernel<<<1, 128, 0, st>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(st, 0, "msm_cube2b_kernel");
+        ChainGaps gaps;
+        for (int i = 0; i < MAX_WINDOWS; i++) gaps.pre[i] = 0;
+        msm_chain_kernel<<<1, 32, 0, st>>>(comp, 1, 1, a1, a2, 0, gaps, 0, acc, partial, (const uint64_t*)ctx->fb_corr); nlaunch++; mark(st, 0, "msm_chain_kernel");
+        ZC_CUDA(ctx, cudaGetLastError());
+        return ZC_OK;
       }
       // Task groups, top-down (local index wl ascends with the window index).  After a group's buckets are
       // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
@@ -949,9 +1055,9 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         // stream, under the next group's accumulation
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
         ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
-        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, side>>>(g_offs, g_hist, seg, gsz, nb, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_fixq_kernel");
+        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, side>>>(g_offs, g_hist, seg, gsz, nb, FIX_INLINE, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_fixq_kernel");
         msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, seg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_heavy_kernel");
-        const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb, seg};
+        const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb, seg, FIX_INLINE};
         // A short (top) window spreads each digit over 2^sub sub-buckets.  sub == A0: the sub-bucket index is exactly the
         // lane digit of the cube, which then simply carries weight 0 (drop).  Otherwise sum the sub-buckets back first.
         uint32_t raw_mask = 0; int drop_wl = -1;
@@ -981,7 +1087,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         for (int i = 1; i < gsz; i++) gaps.pre[i] = c * (tasks[hi - i].w - tasks[hi - 1 - i].w) - A0 - a1 - a2;
         const int gap_post = last ? c * tasks[lo].w : c * (tasks[lo].w - tasks[lo - 1].w) - A0 - a1 - a2;
         msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, drop0, gaps,
-                                             gap_post, acc, last ? partial : nullptr); nlaunch++; mark(chain, 2, "msm_chain_kernel");
+                                             gap_post, acc, last ? partial : nullptr, nullptr); nlaunch++; mark(chain, 2, "msm_chain_kernel");
         hi = lo;
       }
       ZC_CUDA(ctx, cudaEventRecord(ctx->ev[10], chain));
@@ -989,7 +1095,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       ZC_CUDA(ctx, cudaGetLastError());
       return ZC_OK;
     };
-    const zc_msm_key key = {points, scalars, n, c, rank, nranks, use_prepared ? 1 : 0, partial, ctx->msm_ws};
+    const zc_msm_key key = {points, scalars, n, c, rank, nranks, use_fb ? 2 : (use_prepared ? 1 : 0), partial, ctx->msm_ws};
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     ZC_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
     if (cap != cudaStreamCaptureStatusNone || trace) {
@@ -1070,9 +1176,65 @@ int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points, size_t n)
   return ZC_OK;
 }
 
+int32_t zc_msm_prepare_fixed_base_dev(zc_ctx *ctx, const uint64_t *points, size_t n, int32_t window_bits, int32_t rank, int32_t nranks) {
+  if (!ctx) return ZC_ERR_NULL;
+  ZC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!points || n == 0) return zc_fail(ctx, ZC_ERR_NULL, "null / empty points");
+  const int c = window_bits;
+  if (c < 8 || c > 16) return zc_fail(ctx, ZC_ERR_MODE, "window_bits must be in 8..16");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return zc_fail(ctx, ZC_ERR_SIZE, "bad rank / nranks");
+  FbWindows win;
+  win.nwl = 0;
+  const int nwin = (256 + c - 1) / c;
+  for (int w = 0; w < nwin; w++) if (w % nranks == rank) win.w[win.nwl++] = (int16_t)w;
+  for (int t = win.nwl; t < MAX_WINDOWS; t++) win.w[t] = 0;
+  if ((size_t)win.nwl * n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "windows x points exceeds 2^31 - 1");
+  // a recorded graph may hold the old table's address
+  if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
+  ctx->fb_points = nullptr;
+  const size_t need = (size_t)win.nwl * n * 128;
+  if (need > ctx->fb_table_bytes) {
+    if (ctx->fb_table) ZC_CUDA(ctx, cudaFree(ctx->fb_table));
+    ctx->fb_table = nullptr; ctx->fb_table_bytes = 0;
+    ZC_CUDA(ctx, cudaMalloc(&ctx->fb_table, need));
+    ctx->fb_table_bytes = need;
+  }
+  if (win.nwl > 0) {
+    msm_fixed_base_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)ctx->fb_table, n, c, win);
+    ctx->launches++;
+    ZC_CUDA(ctx, cudaGetLastError());
+  }
+  // spread short window (at most one per scalar width): the constant it adds to every MSM, negated, kept for the chain kernel
+  if (ctx->fb_corr) { ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ZC_CUDA(ctx, cudaFree(ctx->fb_corr)); ctx->fb_corr = nullptr; }
+  for (int t = 0; t < win.nwl; t++) {
+    const int sm = merged_spread_bits(c, win.w[t]);
+    if (sm == 0) continue;
+    void *ks = nullptr;
+    int32_t rc;
+    if ((rc = zc_scratch(ctx, 1, n * 40 + 8, &ks))) return rc;
+    ZC_CUDA(ctx, cudaMalloc(&ctx->fb_corr, 160));
+    msm_spread_scalars_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint64_t*)ks, n, sm, c * win.w[t] - sm);
+    ctx->launches++;
+    if ((rc = zc_msm_run(ctx, points, (const uint64_t*)ks, n, c, 0, 1, false, (uint64_t*)ctx->fb_corr))) return rc;
+    if ((rc = zc_point_neg_batch_dev(ctx, (const uint64_t*)ctx->fb_corr, (uint64_t*)ctx->fb_corr, 1))) return rc;
+    if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
+  }
+  ctx->fb_points = points; ctx->fb_n = n; ctx->fb_c = c; ctx->fb_rank = rank; ctx->fb_nranks = nranks;
+  return ZC_OK;
+}
+
 int32_t zc_msm_forget_points(zc_ctx *ctx) {
   if (!ctx) return ZC_ERR_NULL;
+  ZC_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->prep_points = nullptr; ctx->prep_n = 0; ctx->prep_valid = false;
+  if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
+  if (ctx->fb_table) {
+    ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZC_CUDA(ctx, cudaFree(ctx->fb_table));
+  }
+  if (ctx->fb_corr) ZC_CUDA(ctx, cudaFree(ctx->fb_corr));
+  ctx->fb_table = nullptr; ctx->fb_table_bytes = 0; ctx->fb_corr = nullptr;
+  ctx->fb_points = nullptr; ctx->fb_n = 0; ctx->fb_c = 0;
   return ZC_OK;
 }
 

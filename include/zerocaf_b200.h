@@ -170,6 +170,16 @@ int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
 int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t n);
 int32_t zc_msm_forget_points(zc_ctx *ctx);
 
+/* Fixed generators, traded for memory: build the FIXED-BASE TABLES  2^(window_bits * w) * P_i  (affine cached form, 128
+ * bytes per row) for the windows w = rank (mod nranks) -- 16 x n rows at window_bits = 16 on one GPU (2 GiB for 2^20
+ * points), 2 x n rows per rank on 8.  Later zc_msm_dev / zc_msm_partial_dev / zc_msm_sharded_dev calls with the SAME
+ * (points pointer, n, window_bits, rank, nranks) then treat every (window, point) digit as an entry of ONE bucket set:
+ * a single bucket reduction per rank and no doubling chain at all (the serial tail that limits the multi-GPU scaling of
+ * the plain Pippenger path).  For zc_msm_sharded_dev pass the context's own rank / nranks.  One-time cost: c * w_max
+ * doublings + one inversion per row.  Same contract as prepared points (do not modify points[] meanwhile; results
+ * are the same group element); zc_msm_forget_points frees the tables.  Takes precedence over zc_msm_prepare_points_dev. */
+int32_t zc_msm_prepare_fixed_base_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t n, int32_t window_bits, int32_t rank, int32_t nranks);
+
 /* Bucket-window-sharded MSM: a collective, every rank calls it with the same (points, scalars, n, window_bits), all
  * resident on its own device.  Rank r accumulates windows w = r (mod nranks), scales its window sums and folds them to
  * one partial point; the partial points are exchanged ONCE -- over NVLink peer memory (zc_peer_mailbox_*) or with one

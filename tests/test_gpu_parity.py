@@ -501,6 +501,53 @@ def test_msm_prepared_points(zc, oracle):
     assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
 
 
+def test_msm_fixed_base_tables(zc, oracle):
+    """zc_msm_prepare_fixed_base_dev: pre-scaled per-window tables, one merged bucket set, no doubling chain -- the same
+    group element as the naive sum for several window sizes (aligned and not, short top windows), several scalar vectors
+    (incl. the extreme digits of L - 1 and small scalars), sharded over R ranks, and unaffected by other MSMs between."""
+    import torch
+    n = 3000
+    P = synth_points(oracle, 70, n)
+    ctx = zc.default_context()
+    L = ctx._L
+    dP = torch.from_numpy(P.view(np.int64)).cuda()
+    out = torch.zeros(20, dtype=torch.int64, device="cuda")
+    svecs = [oracle.synth_scalar(SEED, 71, 0, n), oracle.synth_scalar(SEED, 72, 0, n)]
+    svecs[1][0] = oracle.int_to_limbs((1 << 249) + 14490550575682688738086195780655237219 - 1)      # L - 1
+    svecs[1][1] = 0
+    svecs[1][2] = oracle.int_to_limbs(1)
+    svecs[1][3] = oracle.int_to_limbs((1 << 249) - 1)
+    want = [oracle.msm_naive(P, s, threads=8) for s in svecs]
+    for c, R in ((16, 1), (13, 1), (8, 1), (11, 1), (16, 2), (16, 8), (12, 3), (16, 32)):
+        for k, s in enumerate(svecs):
+            dS = torch.from_numpy(s.view(np.int64)).cuda()
+            parts = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
+            for r in range(R):
+                ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, c, r, R))
+                ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, r, R, parts[r].data_ptr()))
+                # replay of the recorded graph: the same group element (bucket order is up to the histogram atomics)
+                ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, r, R, out.data_ptr()))
+                ctx.sync()
+                assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), parts[r].cpu().numpy().view(np.uint64)), (c, R, r)
+            ctx.check(L.zc_point_fold_dev(ctx._h, parts.data_ptr(), R, out.data_ptr()))
+            ctx.sync()
+            assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want[k]), (c, R, k)
+    # tables for (c=16, rank 0 of 1); a different shape falls back to the plain path, then the tables are used again
+    ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 16, 0, 1))
+    dS = torch.from_numpy(svecs[0].view(np.int64)).cuda()
+    for c, m in ((16, n), (12, n), (16, 700), (16, n)):
+        ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), m, c, out.data_ptr()))
+        ctx.sync()
+        w = want[0] if m == n else oracle.msm_naive(P[:m], svecs[0][:m], threads=8)
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), w), (c, m)
+    assert L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 17, 0, 1) == 3
+    assert L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 16, 2, 2) == 2
+    ctx.check(L.zc_msm_forget_points(ctx._h))
+    ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want[0])
+
+
 def test_abi_error_convention(zc, oracle):
     """Status codes instead of panics (include/zerocaf_b200.h): argument errors > 0 with a message, n = 0 is a no-op,
     and a failed call leaves the context usable."""

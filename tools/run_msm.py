@@ -19,6 +19,7 @@ ap.add_argument("--rank", type=int, default=0)
 ap.add_argument("--nranks", type=int, default=1)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--prepared", action="store_true")
+ap.add_argument("--fixed-base", action="store_true", help="pre-scaled per-window tables (zc_msm_prepare_fixed_base_dev)")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -35,6 +36,13 @@ out = torch.zeros(20, dtype=torch.int64, device=dev)
 ctx.sync()
 if a.prepared:
     ctx.check(L.zc_msm_prepare_points_dev(ctx._h, P.data_ptr(), n))
+if a.fixed_base:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, P.data_ptr(), n, a.c, a.rank, a.nranks))
+    e1.record(st)
+    st.synchronize()
+    print(f"fixed-base tables rank {a.rank}/{a.nranks}: {e0.elapsed_time(e1):.1f} ms", flush=True)
 for it in range(a.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
@@ -42,6 +50,15 @@ for it in range(a.iters):
     e1.record(st)
     st.synchronize()
     print(f"msm n={n} c={a.c} rank {a.rank}/{a.nranks}: {e0.elapsed_time(e1):.3f} ms", flush=True)
+if a.check and a.fixed_base:
+    # the same MSM through the plain path (no tables) must be the same group element
+    ctx.sync()
+    ref = torch.zeros(20, dtype=torch.int64, device=dev)
+    ctx.check(L.zc_msm_forget_points(ctx._h))
+    ctx.check(L.zc_msm_partial_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, a.c, a.rank, a.nranks, ref.data_ptr()))
+    ctx.sync()
+    eq = zc.batch.ristretto_eq(out.cpu().numpy().view(np.uint64)[None], ref.cpu().numpy().view(np.uint64)[None])
+    print("fixed-base partial == plain partial:", bool(eq[0]))
 if a.check:
     from oracle import oracle as o
     m = min(n, 2048)
