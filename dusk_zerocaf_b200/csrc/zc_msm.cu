@@ -555,141 +555,7 @@ __global__ void __launch_bounds__(256) msm_unfold_kernel(const uint32_t* __restr
   st_pt(buckets + 32 * (size_t)k, p);
 }
 
-// ---- bucket reduction  W = sum_k (k+1) B_k  by digit marginals ("cube" reduction) ----------------------------------
-// Write the bucket index as four digits  k = k3 2^(A0+a1+a2) + k2 2^(A0+a1) + k1 2^A0 + k0  (k0: lane, k1: warp in
-// block, k2 / k3: low / high bits of the block index).  Then
-//     sum_k (k+1) B_k = 2^(A0+a1+a2) sum_v v M3[v] + 2^(A0+a1) sum_v v M2[v] + 2^A0 sum_v v M1[v] + sum_v (v+1) M0[v]
-// where Md[v] is the plain sum of all buckets whose digit d equals v.  Plain sums are trees (depth 5 + a1 in stage 1,
-// <= 8 in stage 2a), every weighted sum has at most 32 terms (stage 2b, depth ~13) and the powers of two are applied
-// for free by the window chain: ~29 dependent point additions instead of ~110 for a chunked running sum.
-constexpr int A0 = 5;
-
-// warp-cooperative weighted sum over n_items <= 32 Q items: lane l owns items l*Q .. l*Q+Q-1.
-//   total = sum_j I_j (lane 0),  weighted = sum_j j I_j (lane 0)
-template <int Q>
-__device__ __forceinline__ void warp_weighted(const uint32_t* __restrict__ items, int n_items, int lane, Pt& total, Pt& weighted) {
-  const int lo = lane * Q;
-  Pt run = pt_identity_mont(), acc = pt_identity_mont();
-#pragma unroll 1
-  for (int j = Q - 1; j >= 0; j--) {
-    const int k = lo + j;
-    if (k < n_items) run = pt_add_ni(run, ld_pt(items + 32 * (size_t)k));
-    if (j > 0) acc = pt_add_ni(acc, run);
-  }
-  Pt S = run;                                  // suffix scan of the lane totals
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    Pt o = shfl_down_pt(S, d);
-    Pt t = pt_add_ni(S, o);
-    if (lane + d < 32) S = t;
-  }
-  Pt z = (lane >= 1) ? S : pt_identity_mont(); // sum_l l c_l = sum_{l >= 1} S_l
-#pragma unroll 1
-  for (int q = Q; q > 1; q >>= 1) z = pt_double_ni(z);
-  if (Q > 1) z = pt_add_ni(z, acc);
-  weighted = warp_sum_pt(z);
-  total = S;
-}
-
-// stage 1: one block per (window, k2): 2^a1 warps x 32 lanes, one bucket per thread.
-//   pm1[blk][warp] = sum over lanes,  pm0[blk][lane] = sum over warps,  tot[blk] = sum of the block's buckets
-// raw_mask: bit wl set = the buckets[] of local window wl (within the group) are final (written by msm_unfold_kernel).
-// Blocks are kept to 128 threads / <= 168 registers so that they fit next to the accumulation's resident blocks.
-__global__ void __launch_bounds__(128, 3) msm_cube1_kernel(BucketSrc src, uint32_t raw_mask, int a1, uint32_t* __restrict__ tot,
-                                                        uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0) {
-  extern __shared__ uint4 cube_sm[];           // [8 uint4 of a point][warp][lane]  +  [8][warp] row sums
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = 1 << a1;
-  const size_t blk = blockIdx.x;
-  uint4* colbuf = cube_sm;
-  uint4* rowbuf = cube_sm + 8 * nw * 32;
-  const size_t gidx = blk * (size_t)(nw * 32) + threadIdx.x;
-  Pt v = ((raw_mask >> (int)(gidx / src.nb)) & 1u) ? ld_pt(src.buckets + 32 * gidx) : load_bucket(src, gidx);
-  auto put = [&](uint4* base, int stride, int idx, const Pt& p) {
-    base[0 * stride + idx] = make_uint4(p.X.w[0], p.X.w[1], p.X.w[2], p.X.w[3]); base[1 * stride + idx] = make_uint4(p.X.w[4], p.X.w[5], p.X.w[6], p.X.w[7]);
-    base[2 * stride + idx] = make_uint4(p.Y.w[0], p.Y.w[1], p.Y.w[2], p.Y.w[3]); base[3 * stride + idx] = make_uint4(p.Y.w[4], p.Y.w[5], p.Y.w[6], p.Y.w[7]);
-    base[4 * stride + idx] = make_uint4(p.Z.w[0], p.Z.w[1], p.Z.w[2], p.Z.w[3]); base[5 * stride + idx] = make_uint4(p.Z.w[4], p.Z.w[5], p.Z.w[6], p.Z.w[7]);
-    base[6 * stride + idx] = make_uint4(p.T.w[0], p.T.w[1], p.T.w[2], p.T.w[3]); base[7 * stride + idx] = make_uint4(p.T.w[4], p.T.w[5], p.T.w[6], p.T.w[7]);
-  };
-  auto get = [&](const uint4* base, int stride, int idx) {
-    Pt p; uint4 q;
-    q = base[0 * stride + idx]; p.X.w[0] = q.x; p.X.w[1] = q.y; p.X.w[2] = q.z; p.X.w[3] = q.w;
-    q = base[1 * stride + idx]; p.X.w[4] = q.x; p.X.w[5] = q.y; p.X.w[6] = q.z; p.X.w[7] = q.w;
-    q = base[2 * stride + idx]; p.Y.w[0] = q.x; p.Y.w[1] = q.y; p.Y.w[2] = q.z; p.Y.w[3] = q.w;
-    q = base[3 * stride + idx]; p.Y.w[4] = q.x; p.Y.w[5] = q.y; p.Y.w[6] = q.z; p.Y.w[7] = q.w;
-    q = base[4 * stride + idx]; p.Z.w[0] = q.x; p.Z.w[1] = q.y; p.Z.w[2] = q.z; p.Z.w[3] = q.w;
-    q = base[5 * stride + idx]; p.Z.w[4] = q.x; p.Z.w[5] = q.y; p.Z.w[6] = q.z; p.Z.w[7] = q.w;
-    q = base[6 * stride + idx]; p.T.w[0] = q.x; p.T.w[1] = q.y; p.T.w[2] = q.z; p.T.w[3] = q.w;
-    q = base[7 * stride + idx]; p.T.w[4] = q.x; p.T.w[5] = q.y; p.T.w[6] = q.z; p.T.w[7] = q.w;
-    return p;
-  };
-  put(colbuf, nw * 32, warp * 32 + lane, v);
-  Pt r = warp_sum_pt(v);                       // row sum (lane 0)
-  if (lane == 0) { st_pt(pm1 + 32 * (blk * nw + warp), r); put(rowbuf, nw, warp, r); }
-  __syncthreads();
-  // column sums over the warps (warp 0 ends up with them) and, on the last warp, the block total from the row sums
-  Pt t = pt_identity_mont();
-  if (warp == nw - 1 && lane < nw) t = get(rowbuf, nw, lane);
-  for (int s2 = nw >> 1; s2 >= 1; s2 >>= 1) {
-    if (warp < s2) {
-      v = pt_add_ni(v, get(colbuf, nw * 32, (warp + s2) * 32 + lane));
-      if (s2 > 1) put(colbuf, nw * 32, warp * 32 + lane, v);
-    } else if (warp == nw - 1) {
-      Pt o = shfl_down_pt(t, s2);
-      t = pt_add_ni(t, o);
-    }
-    __syncthreads();
-  }
-  if (nw == 1) t = r;                          // single warp: total = its row sum
-  if (warp == 0) st_pt(pm0 + 32 * (blk * 32 + lane), v);
-  if (warp == nw - 1 && lane == 0) st_pt(tot + 32 * blk, t);
-}
-
-// stage 2a: one warp per marginal sum.  Tasks of a window: M1[2^a1] and M0[32] over the window's nblk blocks, then
-// M2[2^a2] and M3[2^a3] over the block totals (block index = k3 2^a2 + k2).  marg layout: [M1 | M0 | M2 | M3].
-__global__ void __launch_bounds__(128) msm_cube2a_kernel(const uint32_t* __restrict__ tot, const uint32_t* __restrict__ pm1,
-                                                         const uint32_t* __restrict__ pm0, int a1, int a2, int a3, int nwl,
-                                                         uint32_t* __restrict__ marg) {
-  const int lane = threadIdx.x & 31;
-  const int nw = 1 << a1, n2 = 1 << a2, n3 = 1 << a3, nblk = n2 * n3, ntask = nw + 32 + n2 + n3;
-  const size_t g = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (g >= (size_t)nwl * ntask) return;
-  const size_t wl = g / ntask;
-  const int task = (int)(g - wl * ntask);
-  const uint32_t* base; size_t stride; int count;
-  if (task < nw)                { base = pm1 + 32 * ((wl * nblk) * nw + task);        stride = nw; count = nblk; }
-  else if (task < nw + 32)      { base = pm0 + 32 * ((wl * nblk) * 32 + (task - nw)); stride = 32; count = nblk; }
-  else if (task < nw + 32 + n2) { base = tot + 32 * (wl * nblk + (task - nw - 32));   stride = n2; count = n3; }
-  else                          { base = tot + 32 * (wl * nblk + (size_t)(task - nw - 32 - n2) * n2); stride = 1; count = n2; }
-  Pt acc = pt_identity_mont();
-  bool have = false;
-  for (int b = lane; b < count; b += 32) {
-    Pt x = ld_pt(base + 32 * ((size_t)b * stride));
-    if (!have) { acc = x; have = true; } else acc = pt_add_ni(acc, x);
-  }
-  acc = warp_sum_pt(acc);
-  if (lane == 0) st_pt(marg + 32 * (wl * ntask + task), acc);
-}
-
-// stage 2b: four warps per window: comp[0] = sum v M3[v], comp[1] = sum v M2[v], comp[2] = sum v M1[v],
-// comp[3] = sum (v+1) M0[v]
-// drop_wl: local window (within the launch) whose lane digit k0 is a sub-bucket index (weight (k >> A0) + 1), or -1
-__global__ void __launch_bounds__(128) msm_cube2b_kernel(const uint32_t* __restrict__ marg, int a1, int a2, int a3, int drop_wl, uint32_t* __restrict__ comp) {
-  const int lane = threadIdx.x & 31, which = threadIdx.x >> 5;
-  const int nw = 1 << a1, n2 = 1 << a2, n3 = 1 << a3, ntask = nw + 32 + n2 + n3;
-  const size_t wl = blockIdx.x;
-  const uint32_t* m = marg + 32 * (wl * ntask);
-  Pt total, weighted;
-  if (which == 0)      warp_weighted<1>(m + 32 * (nw + 32 + n2), n3, lane, total, weighted);
-  else if (which == 1) warp_weighted<1>(m + 32 * (nw + 32), n2, lane, total, weighted);
-  else if (which == 2) warp_weighted<1>(m, nw, lane, total, weighted);
-  else {
-    warp_weighted<1>(m + 32 * nw, 32, lane, total, weighted);
-    weighted = ((int)wl == drop_wl) ? total : pt_add_ni(weighted, total);
-  }
-  if (lane == 0) st_pt(comp + 32 * (wl * 4 + which), weighted);
-}
-
-// ---- window chain: acc = 2^(c w) - weighted sum of this rank's window sums, four lanes per point operation ----------
+// ---- four lanes per point operation (window chain and the latency-bound reduction kernels) ---------------------------
 // Lane q = lane & 3 holds coordinate q (X, Y, Z, T) of the running point; the four independent field multiplications
 // of each of the two stages of a doubling / addition run on the four lanes, the operands travel by shuffle.  This
 // turns the strictly serial tail (c doublings per window) from ~8 dependent multiplications per operation into 2.
@@ -780,6 +646,216 @@ __device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
   return quad_stage2(E, F, G, H, q);
 }
 
+
+// ---- bucket reduction  W = sum_k (k+1) B_k  by digit marginals ("cube" reduction) ----------------------------------
+// Write the bucket index as four digits  k = k3 2^(A0+a1+a2) + k2 2^(A0+a1) + k1 2^A0 + k0  (k0: lane, k1: warp in
+// block, k2 / k3: low / high bits of the block index).  Then
+//     sum_k (k+1) B_k = 2^(A0+a1+a2) sum_v v M3[v] + 2^(A0+a1) sum_v v M2[v] + 2^A0 sum_v v M1[v] + sum_v (v+1) M0[v]
+// where Md[v] is the plain sum of all buckets whose digit d equals v.  Plain sums are trees (depth 5 + a1 in stage 1,
+// <= 8 in stage 2a), every weighted sum has at most 32 terms (stage 2b, depth ~13) and the powers of two are applied
+// for free by the window chain: ~29 dependent point additions instead of ~110 for a chunked running sum.
+constexpr int A0 = 5;
+
+// stage 1: one block per (window, k2): 2^a1 warps x 32 lanes, one bucket per thread.
+//   pm1[blk][warp] = sum over lanes,  pm0[blk][lane] = sum over warps,  tot[blk] = sum of the block's buckets
+// raw_mask: bit wl set = the buckets[] of local window wl (within the group) are final (written by msm_unfold_kernel).
+// Blocks are kept to 128 threads / <= 168 registers so that they fit next to the accumulation's resident blocks.
+__global__ void __launch_bounds__(128, 3) msm_cube1_kernel(BucketSrc src, uint32_t raw_mask, int a1, uint32_t* __restrict__ tot,
+                                                        uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0) {
+  extern __shared__ uint4 cube_sm[];           // [8 uint4 of a point][warp][lane]  +  [8][warp] row sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = 1 << a1;
+  const size_t blk = blockIdx.x;
+  uint4* colbuf = cube_sm;
+  uint4* rowbuf = cube_sm + 8 * nw * 32;
+  const size_t gidx = blk * (size_t)(nw * 32) + threadIdx.x;
+  Pt v = ((raw_mask >> (int)(gidx / src.nb)) & 1u) ? ld_pt(src.buckets + 32 * gidx) : load_bucket(src, gidx);
+  auto put = [&](uint4* base, int stride, int idx, const Pt& p) {
+    base[0 * stride + idx] = make_uint4(p.X.w[0], p.X.w[1], p.X.w[2], p.X.w[3]); base[1 * stride + idx] = make_uint4(p.X.w[4], p.X.w[5], p.X.w[6], p.X.w[7]);
+    base[2 * stride + idx] = make_uint4(p.Y.w[0], p.Y.w[1], p.Y.w[2], p.Y.w[3]); base[3 * stride + idx] = make_uint4(p.Y.w[4], p.Y.w[5], p.Y.w[6], p.Y.w[7]);
+    base[4 * stride + idx] = make_uint4(p.Z.w[0], p.Z.w[1], p.Z.w[2], p.Z.w[3]); base[5 * stride + idx] = make_uint4(p.Z.w[4], p.Z.w[5], p.Z.w[6], p.Z.w[7]);
+    base[6 * stride + idx] = make_uint4(p.T.w[0], p.T.w[1], p.T.w[2], p.T.w[3]); base[7 * stride + idx] = make_uint4(p.T.w[4], p.T.w[5], p.T.w[6], p.T.w[7]);
+  };
+  auto get = [&](const uint4* base, int stride, int idx) {
+    Pt p; uint4 q;
+    q = base[0 * stride + idx]; p.X.w[0] = q.x; p.X.w[1] = q.y; p.X.w[2] = q.z; p.X.w[3] = q.w;
+    q = base[1 * stride + idx]; p.X.w[4] = q.x; p.X.w[5] = q.y; p.X.w[6] = q.z; p.X.w[7] = q.w;
+    q = base[2 * stride + idx]; p.Y.w[0] = q.x; p.Y.w[1] = q.y; p.Y.w[2] = q.z; p.Y.w[3] = q.w;
+    q = base[3 * stride + idx]; p.Y.w[4] = q.x; p.Y.w[5] = q.y; p.Y.w[6] = q.z; p.Y.w[7] = q.w;
+    q = base[4 * stride + idx]; p.Z.w[0] = q.x; p.Z.w[1] = q.y; p.Z.w[2] = q.z; p.Z.w[3] = q.w;
+    q = base[5 * stride + idx]; p.Z.w[4] = q.x; p.Z.w[5] = q.y; p.Z.w[6] = q.z; p.Z.w[7] = q.w;
+    q = base[6 * stride + idx]; p.T.w[0] = q.x; p.T.w[1] = q.y; p.T.w[2] = q.z; p.T.w[3] = q.w;
+    q = base[7 * stride + idx]; p.T.w[4] = q.x; p.T.w[5] = q.y; p.T.w[6] = q.z; p.T.w[7] = q.w;
+    return p;
+  };
+  put(colbuf, nw * 32, warp * 32 + lane, v);
+  Pt r = warp_sum_pt(v);                       // row sum (lane 0)
+  if (lane == 0) { st_pt(pm1 + 32 * (blk * nw + warp), r); put(rowbuf, nw, warp, r); }
+  __syncthreads();
+  // column sums over the warps (warp 0 ends up with them) and, on the last warp, the block total from the row sums
+  Pt t = pt_identity_mont();
+  if (warp == nw - 1 && lane < nw) t = get(rowbuf, nw, lane);
+  for (int s2 = nw >> 1; s2 >= 1; s2 >>= 1) {
+    if (warp < s2) {
+      v = pt_add_ni(v, get(colbuf, nw * 32, (warp + s2) * 32 + lane));
+      if (s2 > 1) put(colbuf, nw * 32, warp * 32 + lane, v);
+    } else if (warp == nw - 1) {
+      Pt o = shfl_down_pt(t, s2);
+      t = pt_add_ni(t, o);
+    }
+    __syncthreads();
+  }
+  if (nw == 1) t = r;                          // single warp: total = its row sum
+  if (warp == 0) st_pt(pm0 + 32 * (blk * 32 + lane), v);
+  if (warp == nw - 1 && lane == 0) st_pt(tot + 32 * blk, t);
+}
+
+// Quad helpers for the reduction kernels: a point lives in four consecutive lanes (lane q holds coordinate q), the
+// second operand of an addition is read in full by all four lanes (shared or global memory, a broadcast).  One addition
+// costs three multiplication latencies instead of nine -- these kernels are a few warps of dependent additions each.
+__device__ __forceinline__ Fe ld_coord(const uint32_t* __restrict__ p, int q) { Fe a; ld_fe(p + 8 * q, a); return a; }
+__device__ __forceinline__ void st_coord(uint32_t* __restrict__ p, int q, const Fe& a) { st_fe(p + 8 * q, a); }
+__device__ __forceinline__ Fe identity_coord(int q) {          // (0, 1, 1, 0) in Montgomery form
+  Fe z{{0, 0, 0, 0, 0, 0, 0, 0}};
+  return (q == 1 || q == 2) ? Consts<ModP>::R1() : z;
+}
+// Tree sum over the quads j < n of a block (n a power of two <= blockDim / 4): the result is in quad 0.  sm: n points.
+// Whole warps drop out as the tree narrows (the guard is warp-uniform, quad_add shuffles with a full mask).
+__device__ __forceinline__ Fe quad_block_tree(Fe acc, int n, int j, int q, int qbase, uint32_t* __restrict__ sm) {
+  const int warp = threadIdx.x >> 5;
+  for (int s = n >> 1; s >= 1; s >>= 1) {
+    if (j < 2 * s) st_coord(sm + 32 * j, q, acc);
+    __syncthreads();
+    if (8 * warp < s) {
+      const bool on = j < s;
+      Fe r = quad_add(acc, ld_pt(sm + 32 * (on ? j + s : j)), q, qbase);
+      if (on) acc = r;
+    }
+    __syncthreads();
+  }
+  return acc;
+}
+
+// stage 2a: one block of C2A_QUADS quads per marginal sum.  Tasks of a window: M1[2^a1] and M0[32] over the window's
+// nblk blocks, then M2[2^a2] and M3[2^a3] over the block totals (block index = k3 2^a2 + k2).  marg: [M1 | M0 | M2 | M3].
+constexpr int C2A_QUADS = 64;
+__global__ void __launch_bounds__(4 * C2A_QUADS) msm_cube2a_kernel(const uint32_t* __restrict__ tot, const uint32_t* __restrict__ pm1,
+                                                                   const uint32_t* __restrict__ pm0, int a1, int a2, int a3, int nwl,
+                                                                   uint32_t* __restrict__ marg) {
+  __shared__ __align__(16) uint32_t sm[C2A_QUADS * 32];
+  const int q = threadIdx.x & 3, qbase = threadIdx.x & 28, j = threadIdx.x >> 2;
+  const int nw = 1 << a1, n2 = 1 << a2, n3 = 1 << a3, nblk = n2 * n3, ntask = nw + 32 + n2 + n3;
+  const size_t g = blockIdx.x;
+  const size_t wl = g / ntask;
+  const int task = (int)(g - wl * ntask);
+  const uint32_t* base; size_t stride; int count;
+  if (task < nw)                { base = pm1 + 32 * ((wl * nblk) * nw + task);        stride = nw; count = nblk; }
+  else if (task < nw + 32)      { base = pm0 + 32 * ((wl * nblk) * 32 + (task - nw)); stride = 32; count = nblk; }
+  else if (task < nw + 32 + n2) { base = tot + 32 * (wl * nblk + (task - nw - 32));   stride = n2; count = n3; }
+  else                          { base = tot + 32 * (wl * nblk + (size_t)(task - nw - 32 - n2) * n2); stride = 1; count = n2; }
+  Fe acc = j < count ? ld_coord(base + 32 * ((size_t)j * stride), q) : identity_coord(q);
+  for (int b0 = C2A_QUADS; b0 < count; b0 += C2A_QUADS) {       // count is a power of two: all quads stay busy
+    const int b = b0 + j;
+    acc = quad_add(acc, ld_pt(base + 32 * ((size_t)b * stride)), q, qbase);
+  }
+  const int n = count < C2A_QUADS ? count : C2A_QUADS;
+  acc = quad_block_tree(acc, n, j, q, qbase, sm);
+  if (j == 0) st_coord(marg + 32 * (wl * ntask + task), q, acc);
+}
+
+// stage 2b: one block of 32 quads per component: comp[0] = sum v M3[v], comp[1] = sum v M2[v], comp[2] = sum v M1[v],
+// comp[3] = sum (v+1) M0[v].   sum_v v I_v = sum_{l >= 1} S_l  with the suffix sums S_l = sum_{v >= l} I_v: a scan and a
+// tree, 2 log2(n) additions deep.
+// drop_wl: local window (within the launch) whose lane digit k0 is a sub-bucket index (weight (k >> A0) + 1), or -1
+__global__ void __launch_bounds__(128) msm_cube2b_kernel(const uint32_t* __restrict__ marg, int a1, int a2, int a3, int drop_wl, uint32_t* __restrict__ comp) {
+  __shared__ __align__(16) uint32_t sm[32 * 32];
+  const int q = threadIdx.x & 3, qbase = threadIdx.x & 28, j = threadIdx.x >> 2, warp = threadIdx.x >> 5;
+  const int nw = 1 << a1, n2 = 1 << a2, n3 = 1 << a3, ntask = nw + 32 + n2 + n3;
+  const size_t wl = blockIdx.x >> 2;
+  const int which = blockIdx.x & 3;
+  const uint32_t* m = marg + 32 * (wl * ntask);
+  int n;
+  if (which == 0)      { m += 32 * (nw + 32 + n2); n = n3; }
+  else if (which == 1) { m += 32 * (nw + 32);      n = n2; }
+  else if (which == 2) {                           n = nw; }
+  else                 { m += 32 * nw;             n = 32; }
+  Fe S = j < n ? ld_coord(m + 32 * j, q) : identity_coord(q);
+  for (int d = 1; d < n; d <<= 1) {                              // suffix scan over the quads j < n
+    if (j < n) st_coord(sm + 32 * j, q, S);
+    __syncthreads();
+    if (8 * warp < n) {
+      const bool on = j + d < n;
+      Fe r = quad_add(S, ld_pt(sm + 32 * (on ? j + d : j)), q, qbase);
+      if (on) S = r;
+    }
+    __syncthreads();
+  }
+  const Fe total = S;                                            // quad 0: sum of all items
+  Fe acc = (j >= 1 && j < n) ? S : identity_coord(q);
+  acc = quad_block_tree(acc, n, j, q, qbase, sm);
+  if (which == 3) {
+    if (j == 0) st_coord(sm, q, total);
+    __syncthreads();
+    if (warp == 0) {
+      Fe r = quad_add(acc, ld_pt(sm), q, qbase);
+      acc = ((int)wl == drop_wl) ? total : r;
+    }
+  }
+  if (j == 0) st_coord(comp + 32 * (wl * 4 + which), q, acc);
+}
+
+// Fixed-base path, stage 0: make buckets[] final -- one thread per bucket stitches the partials of a bucket that spans a
+// few segments (the bulk of the work: throughput matters, one lane per bucket) and writes the identity into empty ones.
+__global__ void __launch_bounds__(128) msm_stitch_kernel(BucketSrc src, uint32_t* __restrict__ buckets, size_t total) {
+  const size_t g = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (g >= total) return;
+  const uint32_t cnt = src.hist[g];
+  if (cnt == 0) { st_pt(buckets + 32 * g, pt_identity_mont()); return; }
+  const uint32_t o = src.offs[g], e = o + cnt;
+  const uint32_t s_first = o / (uint32_t)src.seg, s_last = (e - 1) / (uint32_t)src.seg;
+  if (s_first == s_last || s_last - s_first + 1 > (uint32_t)src.fix_inline) return;     // already final
+  st_pt(buckets + 32 * g, load_bucket(src, g));
+}
+// stage 1 with four lanes per bucket (fixed-base path: one bucket set, nothing else on the GPU at that point; the trees
+// are depth-bound).  One block per 128 final buckets (k1 = row 0..3, k0 = column 0..31), 512 threads.  Quads 0..31 form
+// the column sums, quads 32..95 the four row sums (16 quads per row) and the block total.
+__global__ void __launch_bounds__(512) msm_cube1_quad_kernel(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ tot, uint32_t* __restrict__ pm1,
+                                                             uint32_t* __restrict__ pm0) {
+  __shared__ __align__(16) uint32_t sv[128 * 32];               // the block's buckets
+  __shared__ __align__(16) uint32_t sw[64 * 32];                // row trees
+  const int q = threadIdx.x & 3, qbase = threadIdx.x & 28, j = threadIdx.x >> 2, warp = threadIdx.x >> 5;
+  const size_t blk = blockIdx.x;
+  Fe acc = ld_coord(buckets + 32 * (blk * 128 + j), q);
+  st_coord(sv + 32 * j, q, acc);
+  __syncthreads();
+  const int r = j - 32, row = (r >> 4) & 3, i = r & 15;          // quads 32..95: row trees
+  if (warp < 4) {                                                // column sums: quad j = column j
+    for (int k = 1; k < 4; k++) acc = quad_add(acc, ld_pt(sv + 32 * (k * 32 + j)), q, qbase);
+    st_coord(pm0 + 32 * (blk * 32 + j), q, acc);
+  } else if (warp < 12) {
+    acc = quad_add(ld_coord(sv + 32 * (row * 32 + i), q), ld_pt(sv + 32 * (row * 32 + 16 + i)), q, qbase);
+  }
+  for (int s = 8; s >= 1; s >>= 1) {
+    if (warp >= 4 && warp < 12 && i < 2 * s) st_coord(sw + 32 * r, q, acc);
+    __syncthreads();
+    if (warp >= 4 && warp < 12 && (i & 8) == 0) {                // the warp holding i = 0..7 of a row
+      const bool on = i < s;
+      Fe t = quad_add(acc, ld_pt(sw + 32 * (on ? r + s : r)), q, qbase);
+      if (on) acc = t;
+    }
+    __syncthreads();
+  }
+  if (warp >= 4 && warp < 12 && i == 0) {                        // row sums
+    st_coord(pm1 + 32 * (blk * 4 + row), q, acc);
+    st_coord(sw + 32 * row, q, acc);
+  }
+  __syncthreads();
+  if (warp == 4) {                                               // quad 32 (row 0): block total
+    for (int k = 1; k < 4; k++) acc = quad_add(acc, ld_pt(sw + 32 * k), q, qbase);
+    if (j == 32) st_coord(tot + 32 * blk, q, acc);
+  }
+}
+
+// ---- window chain (four lanes per point operation, see the quad helpers above) ---------------------------------------
 // One warp.  acc (in/out, extended Montgomery words) is the running sum, already scaled to 2^(A0+a1+a2) times the unit
 // of this group's top window.  Each window contributes four components (msm_cube2b):
 //   comp0 2^(A0+a1+a2) + comp1 2^(A0+a1) + comp2 2^A0 + comp3.
@@ -871,7 +947,8 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     const int nwb = use_fb ? 1 : nwl;                           // bucket sets
     wmap.merged = use_fb ? 1 : 0;
     const size_t fb_entries = (size_t)nwl * n;
-    const int fb_seg = fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8);
+    static const int fb_seg_env = getenv("ZC_FB_SEG") ? atoi(getenv("ZC_FB_SEG")) : 0;
+    const int fb_seg = fb_seg_env ? fb_seg_env : (fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8));
     // workspace layout
     size_t o = 0;
     size_t o_cached = o; o = align_up(o + (use_fb ? 0 : n * 128), 256);
@@ -975,6 +1052,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     int nstamp = 0;
     auto mark = [&](cudaStream_t s_, int sid, const char* name) {
       if (trace_mode == 2) {
+        if (nstamp == 0) stamp_names.clear();
         if (nstamp < 256) { msm_stamp_kernel<<<1, 1, 0, s_>>>(stamp_buf + nstamp); if ((int)stamp_names.size() <= nstamp) stamp_names.push_back({name, sid}); nstamp++; }
         return;
       }
@@ -1017,10 +1095,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         msm_fixq_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(offs, hist, seg, 1, nb, fix_inline, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_fixq_kernel");
         msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_heavy_kernel");
         const BucketSrc src = {offs, hist, partH, partT, buckets, nseg, nb, seg, fix_inline};
-        const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
-        msm_cube1_kernel<<<(unsigned)nblk, 32 * nw1, cube_smem, st>>>(src, 0u, a1, btot, pm1, pm0); nlaunch++; mark(st, 0, "msm_cube1_kernel");
-        msm_cube2a_kernel<<<(unsigned)((ntask + 3) / 4), 128, 0, st>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(st, 0, "msm_cube2a_kernel");
-        msm_cube2b_kernel<<<1, 128, 0, st>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(st, 0, "msm_cube2b_kernel");
+        msm_stitch_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(src, buckets, (size_t)nb); nlaunch++; mark(st, 0, "msm_stitch_kernel");
+        msm_cube1_quad_kernel<<<(unsigned)nblk, 512, 0, st>>>(buckets, btot, pm1, pm0); nlaunch++; mark(st, 0, "msm_cube1_quad_kernel");
+        msm_cube2a_kernel<<<(unsigned)ntask, 4 * C2A_QUADS, 0, st>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(st, 0, "msm_cube2a_kernel");
+        msm_cube2b_kernel<<<4, 128, 0, st>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(st, 0, "msm_cube2b_kernel");
         ChainGaps gaps;
         for (int i = 0; i < MAX_WINDOWS; i++) gaps.pre[i] = 0;
         msm_chain_kernel<<<1, 32, 0, st>>>(comp, 1, 1, a1, a2, 0, gaps, 0, acc, partial, (const uint64_t*)ctx->fb_corr); nlaunch++; mark(st, 0, "msm_chain_kernel");
@@ -1073,10 +1151,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
         msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, side>>>(src, raw_mask, a1, btot + 32 * ((size_t)lo * nblk),
             pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(side, 1, "msm_cube1_kernel");
-        msm_cube2a_kernel<<<(unsigned)(((size_t)gsz * ntask + 3) / 4), 128, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
+        msm_cube2a_kernel<<<(unsigned)((size_t)gsz * ntask), 4 * C2A_QUADS, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
             pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz,
             marg + 32 * ((size_t)lo * ntask)); nlaunch++; mark(side, 1, "msm_cube2a_kernel");
-        msm_cube2b_kernel<<<gsz, 128, 0, side>>>(marg + 32 * ((size_t)lo * ntask), a1, a2, a3, drop_wl, comp + 128 * (size_t)lo); nlaunch++; mark(side, 1, "msm_cube2b_kernel");
+        msm_cube2b_kernel<<<4 * gsz, 128, 0, side>>>(marg + 32 * ((size_t)lo * ntask), a1, a2, a3, drop_wl, comp + 128 * (size_t)lo); nlaunch++; mark(side, 1, "msm_cube2b_kernel");
         // only the top local window of the whole MSM can be short, i.e. the first window of the first group
         const int drop0 = (drop_wl == gsz - 1) ? A0 : 0;
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[6 + g], side));
