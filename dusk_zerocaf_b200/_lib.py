@@ -84,6 +84,14 @@ def lib():
         getattr(L, "zc_ristretto_elligator_batch" + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_ristretto_from_uniform_bytes_batch" + suf).argtypes = [vp, vp, vp, sz]
         getattr(L, "zc_ristretto_decompress_batch" + suf).argtypes = [vp, vp, vp, vp, sz]
+        for mod in ("fe", "scalar"):
+            getattr(L, f"zc_{mod}_pow_batch{suf}").argtypes = [vp, vp, vp, vp, sz]
+            getattr(L, f"zc_{mod}_half_batch{suf}").argtypes = [vp, vp, vp, sz]
+            getattr(L, f"zc_{mod}_to_bytes_batch{suf}").argtypes = [vp, vp, vp, sz]
+        getattr(L, "zc_fe_from_bytes_batch" + suf).argtypes = [vp, vp, vp, sz]
+        getattr(L, "zc_scalar_from_bytes_batch" + suf).argtypes = [vp, vp, vp, vp, sz]
+        getattr(L, "zc_scalar_window_naf_batch" + suf).argtypes = [vp, vp, i32, vp, sz]
+        getattr(L, "zc_fe_sqrt_ratio_i_batch" + suf).argtypes = [vp, vp, vp, vp, vp, sz]
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
     L.zc_msm_prepare_points_dev.argtypes = [vp, vp, sz]
     L.zc_msm_forget_points.argtypes = [vp]

@@ -146,6 +146,82 @@ def point_is_valid(p, ctx=None):
     return ok
 
 
+def fe_pow(a, e, ctx=None):
+    """Pow for FieldElement (field.rs:334-354): a^e mod p, 0^0 = 1."""
+    return _bin("zc_fe_pow_batch", a, e, 5, ctx)
+
+
+def scalar_pow(a, e, ctx=None):
+    """Pow for Scalar (scalar.rs:293-322): a^e mod L."""
+    return _bin("zc_scalar_pow_batch", a, e, 5, ctx)
+
+
+def fe_half(a, ctx=None):
+    """Half for FieldElement (field.rs:317-323): a * 2^-1 mod p."""
+    return _un("zc_fe_half_batch", a, 5, ctx)
+
+
+def scalar_half(a, ctx=None):
+    """Half for Scalar (scalar.rs:285-291): a * 2^-1 mod L."""
+    return _un("zc_scalar_half_batch", a, 5, ctx)
+
+
+def _to_bytes(name, a, ctx):
+    ctx = ctx or default_context()
+    a = _arr(a, 5)
+    out = np.empty((a.shape[0], 32), dtype=np.uint8)
+    ctx.call(name, a, out, a.shape[0])
+    return out
+
+
+def fe_to_bytes(a, ctx=None):
+    """FieldElement::to_bytes (field.rs:591-631): (n, 32) uint8."""
+    return _to_bytes("zc_fe_to_bytes_batch", a, ctx)
+
+
+def scalar_to_bytes(a, ctx=None):
+    """Scalar::to_bytes (scalar.rs:477-516): (n, 32) uint8."""
+    return _to_bytes("zc_scalar_to_bytes_batch", a, ctx)
+
+
+def fe_from_bytes(data, ctx=None):
+    """FieldElement::from_bytes (field.rs:563-587): all 256 bits kept, no reduction."""
+    ctx = ctx or default_context()
+    d = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+    out = np.empty((d.shape[0], 5), dtype=np.uint64)
+    ctx.call("zc_fe_from_bytes_batch", d, out, d.shape[0])
+    return out
+
+
+def scalar_from_bytes(data, ctx=None):
+    """Scalar::from_bytes (scalar.rs:445-467): ((n, 5) limbs, (n,) ok); ok == 0 where the reference asserts (value >= L)."""
+    ctx = ctx or default_context()
+    d = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+    out = np.empty((d.shape[0], 5), dtype=np.uint64)
+    ok = np.empty(d.shape[0], dtype=np.uint8)
+    ctx.call("zc_scalar_from_bytes_batch", d, out, ok, d.shape[0])
+    return out, ok
+
+
+def scalar_window_naf(a, width, ctx=None):
+    """Scalar::compute_window_NAF (scalar.rs:396-415; width 2 = compute_NAF :370-390): (n, 256) int8, LSB first."""
+    ctx = ctx or default_context()
+    a = _arr(a, 5)
+    out = np.empty((a.shape[0], 256), dtype=np.int8)
+    ctx.check(ctx._L.zc_scalar_window_naf_batch(ctx._h, a.ctypes.data, int(width), out.ctypes.data, a.shape[0]))
+    return out
+
+
+def fe_sqrt_ratio_i(u, v, ctx=None):
+    """FieldElement::sqrt_ratio_i (field.rs:443-491): ((n, 5) root, (n,) was_square)."""
+    ctx = ctx or default_context()
+    u, v = _arr(u, 5), _arr(v, 5)
+    out = np.empty((u.shape[0], 5), dtype=np.uint64)
+    sq = np.empty(u.shape[0], dtype=np.uint8)
+    ctx.call("zc_fe_sqrt_ratio_i_batch", u, v, out, sq, u.shape[0])
+    return out, sq
+
+
 def msm(points, scalars, window_bits=16, ctx=None):
     """sum_i [s_i] P_i as an EdwardsPoint (20 limbs); a group element, compare canonically."""
     ctx = ctx or default_context()

@@ -211,6 +211,19 @@ __device__ __forceinline__ Fe mont_sqrt_ratio_i(const Fe& u, const Fe& v, bool& 
   return r;
 }
 
+// (was_square, r) with r the non-negative root of u/v, or of i u/v when u/v is not a square; (1, 0) for u = 0, (0, 0) for
+// v = 0, u != 0                                                                                      field.rs:443-491
+__global__ void __launch_bounds__(TPB) fe_sqrt_ratio_i_kernel(const uint64_t* __restrict__ u, const uint64_t* __restrict__ v,
+                                                              uint64_t* __restrict__ out, uint8_t* __restrict__ was_square, size_t n) {
+  typedef ModP M;
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  bool sq;
+  Fe r = mont_sqrt_ratio_i(to_mont<M>(fe_load52(u + 5 * i)), to_mont<M>(fe_load52(v + 5 * i)), sq);
+  fe_store52(out + 5 * i, from_mont<M>(r));
+  was_square[i] = sq ? 1 : 0;
+}
+
 // Ristretto-flavoured Elligator 2 on a Montgomery-form r0; the returned (X:Y:Z:T) are the reference's own products
 __device__ __forceinline__ Pt elligator_mont(const Fe& r0) {
   typedef ModP M;
@@ -295,6 +308,30 @@ int32_t zc_fe_invert_batch(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t
   return host_unary(ctx, a, n * 40, out, n * 40, [&](void* di, void* dout) {
     return zc_fe_invert_batch_dev(ctx, (const uint64_t*)di, (uint64_t*)dout, n);
   });
+}
+
+int32_t zc_fe_sqrt_ratio_i_batch_dev(zc_ctx* ctx, const uint64_t* u, const uint64_t* v, uint64_t* out, uint8_t* was_square, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, u && v && out && was_square);
+  fe_sqrt_ratio_i_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(u, v, out, was_square, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_fe_sqrt_ratio_i_batch(zc_ctx* ctx, const uint64_t* u, const uint64_t* v, uint64_t* out, uint8_t* was_square, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, u && v && out && was_square);
+  void *du = nullptr, *dv = nullptr, *dout = nullptr, *dsq = nullptr;
+  int32_t rc;
+  if ((rc = zc_scratch(ctx, 0, n * 40, &du))) return rc;
+  if ((rc = zc_scratch(ctx, 1, n * 40, &dv))) return rc;
+  if ((rc = zc_scratch(ctx, 2, n * 40, &dout))) return rc;
+  if ((rc = zc_scratch(ctx, 3, n, &dsq))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(du, u, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  ZC_CUDA(ctx, cudaMemcpyAsync(dv, v, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = zc_fe_sqrt_ratio_i_batch_dev(ctx, (const uint64_t*)du, (const uint64_t*)dv, (uint64_t*)dout, (uint8_t*)dsq, n))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaMemcpyAsync(was_square, dsq, n, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZC_OK;
 }
 
 int32_t zc_point_to_affine_batch_dev(zc_ctx* ctx, const uint64_t* p, uint64_t* out_xy, size_t n) {

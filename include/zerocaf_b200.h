@@ -155,6 +155,37 @@ int32_t zc_ristretto_from_uniform_bytes_batch_dev(zc_ctx *ctx, const uint8_t *in
 int32_t zc_point_is_valid_batch(zc_ctx *ctx, const uint64_t *p, uint8_t *ok, size_t n);
 int32_t zc_point_is_valid_batch_dev(zc_ctx *ctx, const uint64_t *p, uint8_t *ok, size_t n);
 
+/* ---- vector operations around the MSM: what an inner-product argument does to its scalar vectors
+ * between MSMs, the signed-digit recodings, and the 32-byte wire format of FieldElement / Scalar -------------------------
+ * pow:  out[i] = a[i]^e[i] mod m, 0^0 = 1                   (Pow: field.rs:334-354, scalar.rs:293-322)
+ * half: out[i] = a[i] * 2^-1 mod m                          (Half: field.rs:317-323, scalar.rs:285-291)
+ * to_bytes / from_bytes: [u64;5] limbs <-> 32 little-endian bytes (field.rs:563-631, scalar.rs:445-516).  FieldElement
+ *   from_bytes keeps all 256 bits like the reference; Scalar::from_bytes asserts value <= L - 1 -- here ok[i] = 0 instead
+ *   of a panic (the limbs are still written).  Byte pointers must be 4-byte aligned on the device.
+ * window_naf: 256 signed digits (i8, least significant first) per scalar, width in 2..7; width 2 is compute_NAF
+ *   (scalar.rs:370-415).
+ * sqrt_ratio_i: (was_square[i], out[i]) = FieldElement::sqrt_ratio_i(u[i], v[i])  (field.rs:443-491). */
+int32_t zc_fe_pow_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *e, uint64_t *out, size_t n);
+int32_t zc_fe_pow_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *e, uint64_t *out, size_t n);
+int32_t zc_scalar_pow_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *e, uint64_t *out, size_t n);
+int32_t zc_scalar_pow_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *e, uint64_t *out, size_t n);
+int32_t zc_fe_half_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_fe_half_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_scalar_half_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_scalar_half_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int32_t zc_fe_to_bytes_batch(zc_ctx *ctx, const uint64_t *a, uint8_t *out_bytes, size_t n);
+int32_t zc_fe_to_bytes_batch_dev(zc_ctx *ctx, const uint64_t *a, uint8_t *out_bytes, size_t n);
+int32_t zc_scalar_to_bytes_batch(zc_ctx *ctx, const uint64_t *a, uint8_t *out_bytes, size_t n);
+int32_t zc_scalar_to_bytes_batch_dev(zc_ctx *ctx, const uint64_t *a, uint8_t *out_bytes, size_t n);
+int32_t zc_fe_from_bytes_batch(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out, size_t n);
+int32_t zc_fe_from_bytes_batch_dev(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out, size_t n);
+int32_t zc_scalar_from_bytes_batch(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out, uint8_t *ok, size_t n);
+int32_t zc_scalar_from_bytes_batch_dev(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out, uint8_t *ok, size_t n);
+int32_t zc_scalar_window_naf_batch(zc_ctx *ctx, const uint64_t *a, int32_t width, int8_t *out_digits, size_t n);
+int32_t zc_scalar_window_naf_batch_dev(zc_ctx *ctx, const uint64_t *a, int32_t width, int8_t *out_digits, size_t n);
+int32_t zc_fe_sqrt_ratio_i_batch(zc_ctx *ctx, const uint64_t *u, const uint64_t *v, uint64_t *out, uint8_t *was_square, size_t n);
+int32_t zc_fe_sqrt_ratio_i_batch_dev(zc_ctx *ctx, const uint64_t *u, const uint64_t *v, uint64_t *out, uint8_t *was_square, size_t n);
+
 /* ---- multi-scalar multiplication  out = sum_i [s_i] P_i  (new capability; the reference has none) ---
  * Semantics = fold(Add, identity, [double_and_add(P_i, s_i)]) (edwards.rs:102-120, 465-489) as a GROUP ELEMENT: the
  * returned (X:Y:Z:T) is a valid representative, compare with affine / Ristretto equality.  Pippenger with signed

@@ -19,6 +19,7 @@
 // Where the reference panics (assert! / unwrap) these throw zerocaf::Error; where it returns Option, std::optional.
 #pragma once
 #include <array>
+#include <utility>
 #include <cstdint>
 #include <cstring>
 #include <optional>
@@ -90,6 +91,14 @@ struct FieldElement {
   friend FieldElement operator*(const FieldElement& a, const FieldElement& b) { FieldElement r; Gpu::instance().check(zc_fe_mul_batch(Gpu::instance().ctx(), a.l, b.l, r.l, 1)); return r; }
   FieldElement operator-() const { FieldElement r; Gpu::instance().check(zc_fe_neg_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }
   FieldElement square() const { FieldElement r; Gpu::instance().check(zc_fe_square_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }
+  FieldElement pow(const FieldElement& e) const { FieldElement r; Gpu::instance().check(zc_fe_pow_batch(Gpu::instance().ctx(), l, e.l, r.l, 1)); return r; }   // field.rs:334-354
+  FieldElement half() const { FieldElement r; Gpu::instance().check(zc_fe_half_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }                          // field.rs:317-323
+  // field.rs:443-491: (was_square, root)
+  static std::pair<bool, FieldElement> sqrt_ratio_i(const FieldElement& u, const FieldElement& v) {
+    FieldElement r; uint8_t sq = 0;
+    Gpu::instance().check(zc_fe_sqrt_ratio_i_batch(Gpu::instance().ctx(), u.l, v.l, r.l, &sq, 1));
+    return {sq != 0, r};
+  }
   FieldElement inverse() const {                                          // field.rs:854-925, panics on zero (:864)
     if (*this == zero()) throw Error(ZC_ERR_NONCANONICAL, "FieldElement::inverse of zero");
     FieldElement r; Gpu::instance().check(zc_fe_invert_batch(Gpu::instance().ctx(), l, r.l, 1)); return r;
@@ -118,6 +127,15 @@ struct Scalar {
   friend Scalar operator*(const Scalar& a, const Scalar& b) { Scalar r; Gpu::instance().check(zc_scalar_mul_batch(Gpu::instance().ctx(), a.l, b.l, r.l, 1)); return r; }
   Scalar operator-() const { Scalar r; Gpu::instance().check(zc_scalar_neg_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }
   Scalar square() const { Scalar r; Gpu::instance().check(zc_scalar_square_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }
+  Scalar pow(const Scalar& e) const { Scalar r; Gpu::instance().check(zc_scalar_pow_batch(Gpu::instance().ctx(), l, e.l, r.l, 1)); return r; }   // scalar.rs:293-322
+  Scalar half() const { Scalar r; Gpu::instance().check(zc_scalar_half_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }                    // scalar.rs:285-291
+  // scalar.rs:396-415 (width 2 = compute_NAF :370-390): 256 signed digits, least significant first
+  std::array<int8_t, 256> compute_window_NAF(uint8_t width) const {
+    alignas(4) std::array<int8_t, 256> d;
+    Gpu::instance().check(zc_scalar_window_naf_batch(Gpu::instance().ctx(), l, width, d.data(), 1));
+    return d;
+  }
+  std::array<int8_t, 256> compute_NAF() const { return compute_window_NAF(2); }
   friend bool operator==(const Scalar& a, const Scalar& b) { return a.to_bytes() == b.to_bytes(); }
   friend bool operator!=(const Scalar& a, const Scalar& b) { return !(a == b); }
 };

@@ -548,6 +548,68 @@ def test_msm_fixed_base_tables(zc, oracle):
     assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want[0])
 
 
+def test_vector_ops_pow_half_bytes_naf(zc, oracle, kats):
+    """Pow / Half / to_bytes / from_bytes / window NAF / sqrt_ratio_i through the ABI, bit-exact against
+    the oracle on seeded inputs, edge values and the reference's KATs (field.rs:1262-1269, scalar.rs:913-934, 1023-1052)."""
+    b = zc.batch
+    u64 = lambda *v: np.array(v, dtype=np.uint64)
+    P_INT = (1 << 252) + 27742317777372353535851937790883648493
+    L_INT = (1 << 249) + 14490550575682688738086195780655237219
+    lim = oracle.int_to_limbs
+    # KATs
+    assert np.array_equal(b.fe_pow(F(kats, "A"), F(kats, "C"))[0], F(kats, "A_POW_C"))
+    assert np.array_equal(b.fe_pow(F(kats, "A"), F(kats, "B"))[0], F(kats, "A_POW_B"))
+    assert np.array_equal(b.scalar_pow(S(kats, "A"), S(kats, "B"))[0], S(kats, "A_POW_B"))
+    assert np.array_equal(b.scalar_half(S(kats, "Y"))[0], S(kats, "Y_HALF"))
+    assert np.array_equal(b.scalar_half(S(kats, "A"))[0], u64(0, 0, 0, 1, 0))
+    assert list(b.scalar_window_naf(u64(7, 0, 0, 0, 0), 2)[0][:4]) == [-1, 0, 0, 1]
+    k = u64(1122334455, 0, 0, 0, 0)
+    for w in range(2, 8):
+        assert np.array_equal(b.scalar_window_naf(k, w)[0], oracle.sc_compute_window_naf(k, w)), w
+    # seeded batches + edge values
+    n = 257
+    fa, fe_ = oracle.synth_fe(SEED, 60, 0, n), oracle.synth_fe(SEED, 61, 0, n)
+    sa, se = oracle.synth_scalar(SEED, 62, 0, n), oracle.synth_scalar(SEED, 63, 0, n)
+    for arr, m in ((fa, P_INT), (fe_, P_INT), (sa, L_INT), (se, L_INT)):
+        arr[0] = lim(0); arr[1] = lim(1); arr[2] = lim(m - 1); arr[3] = lim(m - 2); arr[4] = lim(2)
+    fe_[5] = lim(0); fa[5] = lim(0); se[5] = lim(0); sa[5] = lim(0)           # 0^0 = 1
+    assert np.array_equal(b.fe_pow(fa, fe_), np.stack([oracle.fe_pow(fa[i], fe_[i]) for i in range(n)]))
+    assert np.array_equal(b.scalar_pow(sa, se), np.stack([oracle.sc_pow(sa[i], se[i]) for i in range(n)]))
+    assert np.array_equal(b.fe_half(fa), np.stack([oracle.fe_half(x) for x in fa]))
+    assert np.array_equal(b.scalar_half(sa), np.stack([oracle.sc_half(x) for x in sa]))
+    # wire format: to_bytes, from_bytes round trip, Scalar::from_bytes range check
+    fb, sb = b.fe_to_bytes(fa), b.scalar_to_bytes(sa)
+    assert np.array_equal(fb, np.stack([np.frombuffer(oracle.fe_to_bytes(x), dtype=np.uint8) for x in fa]))
+    assert np.array_equal(sb, np.stack([np.frombuffer(oracle.sc_to_bytes(x), dtype=np.uint8) for x in sa]))
+    assert np.array_equal(b.fe_from_bytes(fb), fa)
+    back, ok = b.scalar_from_bytes(sb)
+    assert np.array_equal(back, sa) and ok.all()
+    rnd = np.random.default_rng(7).integers(0, 256, (64, 32), dtype=np.uint8)    # arbitrary 256-bit strings
+    rnd[0] = np.frombuffer(int(L_INT).to_bytes(32, "little"), dtype=np.uint8)     # L itself: rejected
+    rnd[1] = np.frombuffer(int(L_INT - 1).to_bytes(32, "little"), dtype=np.uint8)
+    assert np.array_equal(b.fe_from_bytes(rnd), np.stack([oracle.fe_from_bytes(x) for x in rnd]))
+    got, ok = b.scalar_from_bytes(rnd)
+    for i in range(64):
+        v = int.from_bytes(rnd[i].tobytes(), "little")
+        assert ok[i] == (1 if v < L_INT else 0), i
+        assert oracle.limbs_to_int(got[i]) == v, i
+    # NAF on a batch incl. L - 1 and values next to L (the recoding's k + |d| wraps mod L there)
+    sa[6] = lim(L_INT - 3); sa[7] = lim(L_INT - 5); sa[8] = lim((1 << 249) - 1)
+    for w in (2, 3, 5, 7):
+        assert np.array_equal(b.scalar_window_naf(sa, w), np.stack([oracle.sc_compute_window_naf(x, w) for x in sa])), w
+    ctx = zc.default_context()
+    out = np.empty((1, 256), dtype=np.int8)
+    assert ctx._L.zc_scalar_window_naf_batch(ctx._h, sa.ctypes.data, 8, out.ctypes.data, 1) == 3
+    assert ctx._L.zc_scalar_window_naf_batch(ctx._h, sa.ctypes.data, 1, out.ctypes.data, 1) == 3
+    # sqrt_ratio_i (field.rs:443-491): squares, non-squares, u = 0, v = 0
+    u, v = oracle.synth_fe(SEED, 64, 0, n), oracle.synth_fe(SEED, 65, 0, n)
+    u[0] = lim(0); v[1] = lim(0); u[2] = lim(0); v[2] = lim(0); u[3] = lim(1); v[3] = lim(1); u[4] = lim(4); v[4] = lim(1)
+    r, sq = b.fe_sqrt_ratio_i(u, v)
+    for i in range(n):
+        c, want = oracle.fe_sqrt_ratio_i(u[i], v[i])
+        assert int(sq[i]) == int(c) and np.array_equal(r[i], want), i
+
+
 def test_abi_error_convention(zc, oracle):
     """Status codes instead of panics (include/zerocaf_b200.h): argument errors > 0 with a message, n = 0 is a no-op,
     and a failed call leaves the context usable."""
