@@ -67,7 +67,7 @@ struct zc_ctx {
   zc_msm_key msm_key = {};
   uint64_t msm_graph_launches = 0;
   // MSM: side stream for the window-scaling chain + events (created on first use)
-  cudaStream_t side_stream = nullptr, side_extra[3] = {nullptr, nullptr, nullptr}, chain_stream = nullptr;
+  cudaStream_t side_stream = nullptr, side_extra[3] = {nullptr, nullptr, nullptr}, chain_stream = nullptr, sort_stream = nullptr;
   cudaEvent_t ev[16] = {};
 };
 

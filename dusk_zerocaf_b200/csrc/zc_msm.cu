@@ -628,21 +628,45 @@ __device__ __noinline__ Fe quad_double(Fe c, int q, int qbase) {
   Fe H = fe_sub_lazy<1>(zero, ApB);            // m - (A + B)    in (0, m]
   return quad_stage2(E, F, G, H, q);
 }
-// c (distributed over the quad) += the full point p (every lane holds all of p)
+// a + b without the conditional subtraction (a, b < m: the sum is < 2m < 2^254)
+__device__ __forceinline__ Fe fe_add_lazy(const Fe& a, const Fe& b) {
+  Fe r;
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32    %7, %15, %23;\n\t"
+      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
+      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
+        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
+  return r;
+}
+// c (distributed over the quad) += the full point p (every lane holds all of p; both canonical).  All linear combinations
+// are lazy (< 2m, see above) and computed by every lane before the select: a quad's lanes never branch apart except for
+// lane 3's 2d T2 product.
 __device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
   typedef ModP M;
-  Fe x1 = shfl_fe(c, qbase), y1 = shfl_fe(c, qbase + 1);
+  const Fe x1 = shfl_fe(c, qbase), y1 = shfl_fe(c, qbase + 1);
+  const Fe d1 = fe_sub_lazy<1>(y1, x1), s1 = fe_add_lazy(y1, x1);
+  const Fe d2 = fe_sub_lazy<1>(p.Y, p.X), s2 = fe_add_lazy(p.Y, p.X);
+  const Fe z2 = fe_dbl_lazy(p.Z);
+  Fe t2 = p.T;
+  if (q == 3) t2 = mont_mul<M>(p.T, D2_MONT());
   Fe u, v;
-  if (q == 0)      { u = fe_sub<M>(y1, x1); v = fe_sub<M>(p.Y, p.X); }
-  else if (q == 1) { u = fe_add<M>(y1, x1); v = fe_add<M>(p.Y, p.X); }
-  else if (q == 2) { u = c;                 v = fe_add<M>(p.Z, p.Z); }
-  else             { u = c;                 v = mont_mul<M>(p.T, D2_MONT()); }
-  Fe s = mont_mul<M>(u, v);                                    // A, B, D = 2 Z1 Z2, C = T1 2d T2
-  Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), D = shfl_fe(s, qbase + 2), C = shfl_fe(s, qbase + 3);
-  Fe E = fe_sub<M>(B, A);
-  Fe F = fe_sub<M>(D, C);
-  Fe G = fe_add<M>(D, C);
-  Fe H = fe_add<M>(B, A);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    u.w[k] = q == 0 ? d1.w[k] : (q == 1 ? s1.w[k] : c.w[k]);
+    v.w[k] = q == 0 ? d2.w[k] : (q == 1 ? s2.w[k] : (q == 2 ? z2.w[k] : t2.w[k]));
+  }
+  const Fe s = mont_mul<M>(u, v);                              // A, B, D = 2 Z1 Z2, C = T1 2d T2
+  const Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), D = shfl_fe(s, qbase + 2), C = shfl_fe(s, qbase + 3);
+  const Fe E = fe_sub_lazy<1>(B, A);
+  const Fe F = fe_sub_lazy<1>(D, C);
+  const Fe G = fe_add_lazy(D, C);
+  const Fe H = fe_add_lazy(B, A);
   return quad_stage2(E, F, G, H, q);
 }
 
@@ -804,7 +828,8 @@ __global__ void __launch_bounds__(128) msm_cube2b_kernel(const uint32_t* __restr
 }
 
 // Fixed-base path, stage 0: make buckets[] final -- one thread per bucket stitches the partials of a bucket that spans a
-// few segments (the bulk of the work: throughput matters, one lane per bucket) and writes the identity into empty ones.
+// few segments and writes the identity into empty ones.  (This is the bulk of the reduction's work, throughput matters:
+// one lane per bucket, 38 us for 2^15 buckets of ~5 partials; four lanes per bucket took 52 us.)
 __global__ void __launch_bounds__(128) msm_stitch_kernel(BucketSrc src, uint32_t* __restrict__ buckets, size_t total) {
   const size_t g = (size_t)blockIdx.x * 128 + threadIdx.x;
   if (g >= total) return;
@@ -815,43 +840,47 @@ __global__ void __launch_bounds__(128) msm_stitch_kernel(BucketSrc src, uint32_t
   if (s_first == s_last || s_last - s_first + 1 > (uint32_t)src.fix_inline) return;     // already final
   st_pt(buckets + 32 * g, load_bucket(src, g));
 }
-// stage 1 with four lanes per bucket (fixed-base path: one bucket set, nothing else on the GPU at that point; the trees
-// are depth-bound).  One block per 128 final buckets (k1 = row 0..3, k0 = column 0..31), 512 threads.  Quads 0..31 form
-// the column sums, quads 32..95 the four row sums (16 quads per row) and the block total.
-__global__ void __launch_bounds__(512) msm_cube1_quad_kernel(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ tot, uint32_t* __restrict__ pm1,
-                                                             uint32_t* __restrict__ pm0) {
+// stage 1 with four lanes per point (fixed-base path: one bucket set, nothing else on the GPU at that point; the trees
+// are depth-bound).  One block of 64 quads per 128 final buckets (k1 = row 0..3, k0 = column 0..31).  Every quad starts
+// in a row tree (16 quads per row); the quads that drop out of it first take the 32 column sums while quad 0 adds up
+// the block total.
+__global__ void __launch_bounds__(256) msm_cube1_quad_kernel(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ tot,
+                                                             uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0) {
   __shared__ __align__(16) uint32_t sv[128 * 32];               // the block's buckets
   __shared__ __align__(16) uint32_t sw[64 * 32];                // row trees
   const int q = threadIdx.x & 3, qbase = threadIdx.x & 28, j = threadIdx.x >> 2, warp = threadIdx.x >> 5;
   const size_t blk = blockIdx.x;
-  Fe acc = ld_coord(buckets + 32 * (blk * 128 + j), q);
-  st_coord(sv + 32 * j, q, acc);
-  __syncthreads();
-  const int r = j - 32, row = (r >> 4) & 3, i = r & 15;          // quads 32..95: row trees
-  if (warp < 4) {                                                // column sums: quad j = column j
-    for (int k = 1; k < 4; k++) acc = quad_add(acc, ld_pt(sv + 32 * (k * 32 + j)), q, qbase);
-    st_coord(pm0 + 32 * (blk * 32 + j), q, acc);
-  } else if (warp < 12) {
-    acc = quad_add(ld_coord(sv + 32 * (row * 32 + i), q), ld_pt(sv + 32 * (row * 32 + 16 + i)), q, qbase);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(buckets + 32 * (blk * 128));
+    uint4* dst = reinterpret_cast<uint4*>(sv);
+    for (int k = threadIdx.x; k < 128 * 8; k += 256) dst[k] = src[k];
   }
+  __syncthreads();
+  const int row = j >> 4, i = j & 15;
+  Fe acc = quad_add(ld_coord(sv + 32 * (row * 32 + i), q), ld_pt(sv + 32 * (row * 32 + 16 + i)), q, qbase);
   for (int s = 8; s >= 1; s >>= 1) {
-    if (warp >= 4 && warp < 12 && i < 2 * s) st_coord(sw + 32 * r, q, acc);
+    if (i < 2 * s) st_coord(sw + 32 * j, q, acc);
     __syncthreads();
-    if (warp >= 4 && warp < 12 && (i & 8) == 0) {                // the warp holding i = 0..7 of a row
+    if ((i & 8) == 0) {                                          // even warps: i = 0..7 of a row
       const bool on = i < s;
-      Fe t = quad_add(acc, ld_pt(sw + 32 * (on ? r + s : r)), q, qbase);
+      const Fe t = quad_add(acc, ld_pt(sw + 32 * (on ? j + s : j)), q, qbase);
       if (on) acc = t;
     }
     __syncthreads();
   }
-  if (warp >= 4 && warp < 12 && i == 0) {                        // row sums
+  if (i == 0) {                                                  // row sums
     st_coord(pm1 + 32 * (blk * 4 + row), q, acc);
     st_coord(sw + 32 * row, q, acc);
   }
   __syncthreads();
-  if (warp == 4) {                                               // quad 32 (row 0): block total
+  if (warp == 0) {                                               // quad 0 (row 0): block total
     for (int k = 1; k < 4; k++) acc = quad_add(acc, ld_pt(sw + 32 * k), q, qbase);
-    if (j == 32) st_coord(tot + 32 * blk, q, acc);
+    if (j == 0) st_coord(tot + 32 * blk, q, acc);
+  } else if (warp & 1) {                                         // the 32 quads with i >= 8: one column each
+    const int col = (warp >> 1) * 8 + (i & 7);
+    Fe cs = ld_coord(sv + 32 * col, q);
+    for (int k = 1; k < 4; k++) cs = quad_add(cs, ld_pt(sv + 32 * (k * 32 + col)), q, qbase);
+    st_coord(pm0 + 32 * (blk * 32 + col), q, cs);
   }
 }
 
@@ -1019,6 +1048,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       for (int i = 0; i < 2; i++) ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_extra[i], cudaStreamNonBlocking, prio_lo));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_extra[2], cudaStreamNonBlocking, prio_hi));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, prio_hi));
+      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sort_stream, cudaStreamNonBlocking, prio_lo));
       for (int i = 0; i < 16; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     }
     // st: digits, sort, accumulation.  sides[g % 4]: operand preparation (sides[0]), then stitch + reduce of group g --
@@ -1069,20 +1099,46 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++; mark(side, 1, "msm_prep_kernel");
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[1], side));
       }
-      {
+      // digits + histogram, scan, scatter of the local windows [lo, hi) on stream s_
+      auto sort_windows = [&](cudaStream_t s_, int sid, int lo, int hi) {
+        WinMap m = wmap;
+        for (int w = 0; w < MAX_WINDOWS; w++) if (m.tl[w] < lo || m.tl[w] >= hi) m.tl[w] = -1;
         const unsigned grid = (unsigned)((n + 255) / 256);
         switch (c) {
-#define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, st>>>(scalars, n, wmap, digits, ranks, hist); break;
+#define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, s_>>>(scalars, n, m, digits, ranks, hist); break;
           ZC_DIGITS_CASE(8) ZC_DIGITS_CASE(9) ZC_DIGITS_CASE(10) ZC_DIGITS_CASE(11) ZC_DIGITS_CASE(12)
           ZC_DIGITS_CASE(13) ZC_DIGITS_CASE(14) ZC_DIGITS_CASE(15) ZC_DIGITS_CASE(16)
 #undef ZC_DIGITS_CASE
         }
-        nlaunch++; mark(st, 0, "msm_digits_kernel");
-      }
-      msm_scan_kernel<<<nwb, SCAN_TPB, 0, st>>>(hist, offs, nb); nlaunch++; mark(st, 0, "msm_scan_kernel");
-      {
-        size_t tot = n * (size_t)nwl;
-        msm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(digits, ranks, n, n_pad, nwl, nb, use_fb ? 1 : 0, offs, sorted); nlaunch++; mark(st, 0, "msm_scatter_kernel");
+        nlaunch++; mark(s_, sid, "msm_digits_kernel");
+        if (use_fb) {
+          msm_scan_kernel<<<1, SCAN_TPB, 0, s_>>>(hist, offs, nb); nlaunch++; mark(s_, sid, "msm_scan_kernel");
+          msm_scatter_kernel<<<(unsigned)((n * (size_t)nwl + 255) / 256), 256, 0, s_>>>(digits, ranks, n, n_pad, nwl, nb, 1, offs, sorted);
+        } else {
+          msm_scan_kernel<<<hi - lo, SCAN_TPB, 0, s_>>>(hist + (size_t)lo * nb, offs + (size_t)lo * nb, nb); nlaunch++; mark(s_, sid, "msm_scan_kernel");
+          msm_scatter_kernel<<<(unsigned)((n * (size_t)(hi - lo) + 255) / 256), 256, 0, s_>>>(digits + (size_t)lo * n, ranks + (size_t)lo * n, n, n_pad,
+              hi - lo, nb, 0, offs + (size_t)lo * nb, sorted + (size_t)lo * n_pad);
+        }
+        nlaunch++; mark(s_, sid, "msm_scatter_kernel");
+      };
+      // Task groups, top-down (local index wl ascends with the window index)
+      const int ngroups = nwl < MAX_GROUPS ? nwl : MAX_GROUPS;
+      int glo[MAX_GROUPS], ghi[MAX_GROUPS];
+      for (int g = 0, h = nwl; g < ngroups; g++) { const int gsz = (h + (ngroups - g) - 1) / (ngroups - g); ghi[g] = h; glo[g] = h - gsz; h -= gsz; }
+      // The sort of a group is atomics / scattered stores, its accumulation is multiplier-bound: the groups' sorts run on
+      // their own stream, one or more groups ahead of the accumulation (2^20 points on one GPU: 0.4 ms of sorting, three
+      // quarters of it hidden).
+      static const bool pipe_sort_env = !(getenv("ZC_MSM_PIPE_SORT") && atoi(getenv("ZC_MSM_PIPE_SORT")) == 0);
+      const bool pipe_sort = pipe_sort_env && !use_fb && ngroups > 1;
+      if (pipe_sort) {
+        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[15], st));
+        ZC_CUDA(ctx, cudaStreamWaitEvent(ctx->sort_stream, ctx->ev[15], 0));
+        for (int g = 0; g < ngroups; g++) {
+          sort_windows(ctx->sort_stream, 3, glo[g], ghi[g]);
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[11 + g], ctx->sort_stream));
+        }
+      } else {
+        sort_windows(st, 0, 0, nwl);
       }
       if (use_fb) {
         // one bucket set over all (window, point) entries: accumulate, stitch, reduce, combine the four cube components
@@ -1096,7 +1152,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_heavy_kernel");
         const BucketSrc src = {offs, hist, partH, partT, buckets, nseg, nb, seg, fix_inline};
         msm_stitch_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(src, buckets, (size_t)nb); nlaunch++; mark(st, 0, "msm_stitch_kernel");
-        msm_cube1_quad_kernel<<<(unsigned)nblk, 512, 0, st>>>(buckets, btot, pm1, pm0); nlaunch++; mark(st, 0, "msm_cube1_quad_kernel");
+        msm_cube1_quad_kernel<<<(unsigned)nblk, 256, 0, st>>>(buckets, btot, pm1, pm0); nlaunch++; mark(st, 0, "msm_cube1_quad_kernel");
         msm_cube2a_kernel<<<(unsigned)ntask, 4 * C2A_QUADS, 0, st>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(st, 0, "msm_cube2a_kernel");
         msm_cube2b_kernel<<<4, 128, 0, st>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(st, 0, "msm_cube2b_kernel");
         ChainGaps gaps;
@@ -1108,12 +1164,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       // Task groups, top-down (local index wl ascends with the window index).  After a group's buckets are
       // accumulated the side stream stitches and reduces them, folds the window sums into acc and scales acc down to the
       // next group's top window (or, after the last group, by 2^(c * rank)) while the main stream accumulates the next group.
-      const int ngroups = nwl < MAX_GROUPS ? nwl : MAX_GROUPS;
-      int hi = nwl;
       for (int g = 0; g < ngroups; g++) {
         side = (g == ngroups - 1) ? sides[3] : sides[g % 3];
-        const int gsz = (hi + (ngroups - g) - 1) / (ngroups - g);
-        const int lo = hi - gsz;
+        const int hi = ghi[g], lo = glo[g], gsz = hi - lo;
+        if (pipe_sort) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[11 + g], 0));                 // this group's entries are sorted
         size_t group_entries = 0;
         for (int wl = lo; wl < hi; wl++) group_entries += tasks[wl].p1 - tasks[wl].p0;
         const int seg = group_entries >= ((size_t)1 << 22) ? 32 : (group_entries > ((size_t)1 << 19) ? 16 : 8);
@@ -1166,7 +1220,6 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         const int gap_post = last ? c * tasks[lo].w : c * (tasks[lo].w - tasks[lo - 1].w) - A0 - a1 - a2;
         msm_chain_kernel<<<1, 32, 0, chain>>>(comp + 128 * (size_t)(hi - 1), gsz, g == 0 ? 1 : 0, a1, a2, drop0, gaps,
                                              gap_post, acc, last ? partial : nullptr, nullptr); nlaunch++; mark(chain, 2, "msm_chain_kernel");
-        hi = lo;
       }
       ZC_CUDA(ctx, cudaEventRecord(ctx->ev[10], chain));
       ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[10], 0));
