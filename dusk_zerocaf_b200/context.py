@@ -84,6 +84,20 @@ class Context:
         self.check(self._L.zc_peer_mailbox_connect(self._h, ctypes.cast(allb, ctypes.c_void_p), int(rank), int(nranks)))
 
 
+    # ---- fixed generators --------------------------------------------------------------------------------------
+    def msm_prepare_points(self, points_dev_ptr, n):
+        """zc_msm_prepare_points_dev: cache the MSM operands of a resident point set (Z = 1, cached form)."""
+        self.check(self._L.zc_msm_prepare_points_dev(self._h, points_dev_ptr, int(n)))
+
+    def msm_prepare_fixed_base(self, points_dev_ptr, n, window_bits=16, rank=0, nranks=1):
+        """zc_msm_prepare_fixed_base_dev: pre-scaled rows 2^(c w) P_i for the windows rank owns (one merged bucket set and
+        no doubling chain in later MSM calls of this shape)."""
+        self.check(self._L.zc_msm_prepare_fixed_base_dev(self._h, points_dev_ptr, int(n), int(window_bits), int(rank), int(nranks)))
+
+    def msm_forget_points(self):
+        self.check(self._L.zc_msm_forget_points(self._h))
+
+
 _default = None
 
 

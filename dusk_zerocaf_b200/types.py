@@ -77,6 +77,17 @@ class FieldElement(_Residue):
     _ops = (batch.fe_mul, batch.fe_add, batch.fe_sub, batch.fe_square, batch.fe_neg)
 
     def __mul__(self, o): return self._b(0, o)
+    def pow(self, e): return FieldElement(batch.fe_pow(self.limbs, e.limbs)[0])            # field.rs:334-354
+    def half(self): return FieldElement(batch.fe_half(self.limbs)[0])                      # field.rs:317-323
+    def inverse(self):                                                                     # field.rs:854-925
+        if self == FieldElement.zero():
+            raise ZeroDivisionError("FieldElement::inverse of zero (the reference asserts, field.rs:864)")
+        return FieldElement(batch.fe_invert(self.limbs)[0])
+
+    @staticmethod
+    def sqrt_ratio_i(u, v):                                                                # field.rs:443-491
+        r, sq = batch.fe_sqrt_ratio_i(u.limbs, v.limbs)
+        return bool(sq[0]), FieldElement(r[0])
 
 
 class Scalar(_Residue):
@@ -93,6 +104,11 @@ class Scalar(_Residue):
         if isinstance(o, (EdwardsPoint, RistrettoPoint)):   # Mul<EdwardsPoint> for Scalar (edwards.rs:563-577)
             return o * self
         return self._b(0, o)
+
+    def pow(self, e): return Scalar(batch.scalar_pow(self.limbs, e.limbs)[0])              # scalar.rs:293-322
+    def half(self): return Scalar(batch.scalar_half(self.limbs)[0])                        # scalar.rs:285-291
+    def compute_window_NAF(self, width): return batch.scalar_window_naf(self.limbs, width)[0]   # scalar.rs:396-415
+    def compute_NAF(self): return self.compute_window_NAF(2)                               # scalar.rs:370-390
 
 
 class EdwardsPoint:

@@ -640,6 +640,17 @@ def test_operator_surface(zc, kats, oracle):
     assert (A - B) == zc.FieldElement(F(kats, "A_MINUS_B"))
     assert (-A) == zc.FieldElement(F(kats, "MINUS_A"))
     assert A.square() == zc.FieldElement(F(kats, "A_SQUARE"))
+    assert A.pow(B) == zc.FieldElement(F(kats, "A_POW_B"))                  # a_pow_b field.rs:1262
+    assert A.inverse() == zc.FieldElement(F(kats, "INV_MOD_A"))             # savas_koc_inverse :1531
+    assert A.half() + A.half() == A
+    ok, root = zc.FieldElement.sqrt_ratio_i(A.square(), zc.FieldElement.one())
+    assert ok and root.square() == A.square()
+    with pytest.raises(ZeroDivisionError):
+        zc.FieldElement.zero().inverse()
+    SA, SB, SY = zc.Scalar(S(kats, "A")), zc.Scalar(S(kats, "B")), zc.Scalar(S(kats, "Y"))
+    assert SA.pow(SB) == zc.Scalar(S(kats, "A_POW_B"))                      # mod_pow scalar.rs:929
+    assert SY.half() == zc.Scalar(S(kats, "Y_HALF"))                        # half :913
+    assert list(zc.Scalar(oracle.int_to_limbs(7)).compute_NAF()[:4]) == [-1, 0, 0, 1]   # naf :1023
     P1, P2 = zc.EdwardsPoint(E(kats, "P1_EXTENDED")), zc.EdwardsPoint(E(kats, "P2_EXTENDED"))
     assert np.array_equal((P1 + P2).limbs, E(kats, "P4_EXTENDED"))
     assert P1.double() == zc.EdwardsPoint(E(kats, "P3_EXTENDED"))
