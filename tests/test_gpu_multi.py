@@ -1,5 +1,6 @@
 """Sharded MSM on two real GPUs (skipped on a single-GPU box): one process per GPU, exchange over NVLink peer-memory
-mailboxes and over NCCL, both against this rank's own single-GPU MSM; identical bits on both ranks."""
+mailboxes and over NCCL, then with prepared points and with fixed-base tables, each against this rank's own single-GPU
+MSM; identical bits on both ranks."""
 import os
 import socket
 
@@ -47,9 +48,13 @@ def _worker(rank, world, port, q):
 
     results = []
     ctx.init_nccl(rank, world, bcast)
-    for path in ("nccl", "peer"):
+    for path in ("nccl", "peer", "peer+prepared", "peer+fixed_base"):
         if path == "peer":
             ctx.init_peer_mailboxes(rank, world, allgather)
+        elif path == "peer+prepared":
+            ctx.msm_prepare_points(P.data_ptr(), n)
+        elif path == "peer+fixed_base":
+            ctx.msm_prepare_fixed_base(P.data_ptr(), n, c, rank, world)
         out = torch.zeros(20, dtype=torch.int64, device=dev)
         for _ in range(3):                                               # repeated calls: sequence numbers / graph replay
             ctx.check(L.zc_msm_sharded_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, c, out.data_ptr()))
@@ -81,5 +86,5 @@ def test_sharded_msm_two_gpus_peer_and_nccl():
     for r in range(world):
         for path, ok, _ in res[r]:
             assert ok, (r, path)
-    for k in range(2):
-        assert res[0][k][2] == res[1][k][2], res[0][k][0]            # identical bits on all ranks, per exchange path
+    for k in range(len(res[0])):
+        assert res[0][k][2] == res[1][k][2], res[0][k][0]            # identical bits on all ranks, per path
