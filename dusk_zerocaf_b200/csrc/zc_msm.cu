@@ -1193,6 +1193,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         // A short (top) window spreads each digit over 2^sub sub-buckets.  sub == A0: the sub-bucket index is exactly the
         // lane digit of the cube, which then simply carries weight 0 (drop).  Otherwise sum the sub-buckets back first.
         uint32_t raw_mask = 0; int drop_wl = -1;
+        // stage 1 either stitches on load (msm_cube1_kernel, one bucket per thread) or, like the fixed-base path, reads buckets
+        // made final by a stitch pass and runs its trees with four lanes per point.  ZC_MSM_QUAD_STAGE1: 0 never, 1 every
+        // group (default), 2 only the last group.  Measured at 2^20 points on one GPU: 3.40 / 3.23 / 3.30 ms -- the
+        // reductions share the SMs with the next group's accumulation, so their total SM time matters, not only their depth.
+        static const int quad_stage1_env = getenv("ZC_MSM_QUAD_STAGE1") ? atoi(getenv("ZC_MSM_QUAD_STAGE1")) : 1;
+        const bool quad_stage1 = quad_stage1_env == 1 || (quad_stage1_env == 2 && g == ngroups - 1);
+        if (quad_stage1) { msm_stitch_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, side>>>(src, g_buckets, tot); nlaunch++; mark(side, 1, "msm_stitch_kernel"); }
         for (int wl = lo; wl < hi; wl++) {
           const int sub = short_window_sub_bits(c, tasks[wl].w);
           if (sub == A0 && g == 0 && wl == hi - 1) drop_wl = wl - lo;
@@ -1203,8 +1210,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
           }
         }
         const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
-        msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, side>>>(src, raw_mask, a1, btot + 32 * ((size_t)lo * nblk),
-            pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(side, 1, "msm_cube1_kernel");
+        if (quad_stage1) {
+          msm_cube1_quad_kernel<<<(unsigned)((size_t)gsz * nblk), 256, 0, side>>>(g_buckets, btot + 32 * ((size_t)lo * nblk),
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(side, 1, "msm_cube1_quad_kernel");
+        } else {
+          msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, side>>>(src, raw_mask, a1, btot + 32 * ((size_t)lo * nblk),
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(side, 1, "msm_cube1_kernel");
+        }
         msm_cube2a_kernel<<<(unsigned)((size_t)gsz * ntask), 4 * C2A_QUADS, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
             pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz,
             marg + 32 * ((size_t)lo * ntask)); nlaunch++; mark(side, 1, "msm_cube2a_kernel");
