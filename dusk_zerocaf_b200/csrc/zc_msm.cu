@@ -55,6 +55,63 @@ __device__ __forceinline__ void st_pt(uint32_t* __restrict__ p, const Pt& a) {
 __device__ __forceinline__ Fe DINV_MONT() {
   return Fe{{0x69c50bb0u, 0xa53327e2u, 0x96b47422u, 0xeaa0ffd5u, 0xfd35fb8fu, 0xd34f1e03u, 0x8d35344bu, 0x0b7245f4u}};
 }
+// lazy linear combinations (bucket accumulation, window chain, reduction trees): no conditional subtraction, results < 4m (inputs canonical);
+// mont_mul accepts them because the product of any two stays below R m = 2^256 m (16 m^2 > 8 m^2).
+__device__ __forceinline__ Fe fe_dbl_lazy(const Fe& a) {                 // 2a < 2m
+  Fe r;
+#pragma unroll
+  for (int k = 7; k > 0; k--) r.w[k] = __funnelshift_l(a.w[k - 1], a.w[k], 1);
+  r.w[0] = a.w[0] << 1;
+  return r;
+}
+// a - b + K m  (K = 1 or 2), a < K' m, b < K m
+template <int K>
+__device__ __forceinline__ Fe fe_sub_lazy(const Fe& a, const Fe& b) {
+  typedef ModP M;
+  constexpr uint64_t m01 = ((uint64_t)M::M1 << 32 | M::M0), m23 = ((uint64_t)M::M3 << 32 | M::M2);
+  // K * m as words (K <= 2: no overflow of the 4 low words into word 4 beyond a carry)
+  constexpr unsigned __int128 lowK = ((unsigned __int128)m23 << 64 | m01) * K;
+  constexpr uint32_t k0 = (uint32_t)lowK, k1 = (uint32_t)(lowK >> 32), k2 = (uint32_t)(lowK >> 64), k3 = (uint32_t)(lowK >> 96),
+                     k4 = (uint32_t)(lowK >> 128), k7 = M::M7 * K;
+  Fe r;
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, 0;\n\t"
+      "addc.cc.u32 %6, %14, 0;\n\t"
+      "addc.u32    %7, %15, %21;\n\t"
+      "sub.cc.u32  %0, %0, %22;\n\t"
+      "subc.cc.u32 %1, %1, %23;\n\t"
+      "subc.cc.u32 %2, %2, %24;\n\t"
+      "subc.cc.u32 %3, %3, %25;\n\t"
+      "subc.cc.u32 %4, %4, %26;\n\t"
+      "subc.cc.u32 %5, %5, %27;\n\t"
+      "subc.cc.u32 %6, %6, %28;\n\t"
+      "subc.u32    %7, %7, %29;\n\t"
+      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
+      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
+        "r"(k0), "r"(k1), "r"(k2), "r"(k3), "r"(k4), "r"(k7),
+        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
+  return r;
+}
+// a + b without the conditional subtraction (a, b < m: the sum is < 2m < 2^254)
+__device__ __forceinline__ Fe fe_add_lazy(const Fe& a, const Fe& b) {
+  Fe r;
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32    %7, %15, %23;\n\t"
+      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
+      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
+        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
+  return r;
+}
 // ---- prep ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msm_prep_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
   size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -316,17 +373,20 @@ __device__ __noinline__ Fe acc_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
 template <bool AFFINE>
 __device__ __forceinline__ Pt pt_add_staged(const Pt& p, const uint4* __restrict__ q, bool neg) {
   typedef ModP M;
-  Fe A = acc_mul(fe_sub<M>(p.Y, p.X), lds_fe(q + (neg ? 0 : 2) * ACC_TPB));
-  Fe B = acc_mul(fe_add<M>(p.Y, p.X), lds_fe(q + (neg ? 2 : 0) * ACC_TPB));
+  // p and the staged operand are canonical; every linear combination below is lazy (no conditional subtraction): the
+  // factors stay below 2m, 2m, 3m, 3m and each product below 9 m^2 < R m, which is all the Montgomery product needs
+  const Fe zero{{0, 0, 0, 0, 0, 0, 0, 0}};
+  Fe A = acc_mul(fe_sub_lazy<1>(p.Y, p.X), lds_fe(q + (neg ? 0 : 2) * ACC_TPB));
+  Fe B = acc_mul(fe_add_lazy(p.Y, p.X), lds_fe(q + (neg ? 2 : 0) * ACC_TPB));
   Fe t2d = lds_fe(q + 6 * ACC_TPB);
-  if (neg) t2d = fe_neg<M>(t2d);
+  if (neg) t2d = fe_sub_lazy<1>(zero, t2d);                    // m - 2dT2 in (0, m]
   Fe C = acc_mul(p.T, t2d);
   Fe D = AFFINE ? p.Z : acc_mul(p.Z, lds_fe(q + 4 * ACC_TPB));
-  D = fe_add<M>(D, D);
-  Fe E = fe_sub<M>(B, A);
-  Fe F = fe_sub<M>(D, C);
-  Fe G = fe_add<M>(D, C);
-  Fe H = fe_add<M>(B, A);
+  D = fe_dbl_lazy(D);                                          // < 2m
+  Fe E = fe_sub_lazy<1>(B, A);                                 // < 2m
+  Fe F = fe_sub_lazy<1>(D, C);                                 // < 3m
+  Fe G = fe_add_lazy(D, C);                                    // < 3m
+  Fe H = fe_add_lazy(B, A);                                    // < 2m
   Pt r;
   r.X = acc_mul(E, F);
   r.Y = acc_mul(G, H);
@@ -570,47 +630,6 @@ __device__ __forceinline__ Fe quad_stage2(const Fe& E, const Fe& F, const Fe& G,
   }
   return mont_mul<M>(u, v);
 }
-// lazy linear combinations for the chain: no conditional subtraction, results < 4m (inputs canonical);
-// mont_mul accepts them because the product of any two stays below R m = 2^256 m (16 m^2 > 8 m^2).
-__device__ __forceinline__ Fe fe_dbl_lazy(const Fe& a) {                 // 2a < 2m
-  Fe r;
-#pragma unroll
-  for (int k = 7; k > 0; k--) r.w[k] = __funnelshift_l(a.w[k - 1], a.w[k], 1);
-  r.w[0] = a.w[0] << 1;
-  return r;
-}
-// a - b + K m  (K = 1 or 2), a < K' m, b < K m
-template <int K>
-__device__ __forceinline__ Fe fe_sub_lazy(const Fe& a, const Fe& b) {
-  typedef ModP M;
-  constexpr uint64_t m01 = ((uint64_t)M::M1 << 32 | M::M0), m23 = ((uint64_t)M::M3 << 32 | M::M2);
-  // K * m as words (K <= 2: no overflow of the 4 low words into word 4 beyond a carry)
-  constexpr unsigned __int128 lowK = ((unsigned __int128)m23 << 64 | m01) * K;
-  constexpr uint32_t k0 = (uint32_t)lowK, k1 = (uint32_t)(lowK >> 32), k2 = (uint32_t)(lowK >> 64), k3 = (uint32_t)(lowK >> 96),
-                     k4 = (uint32_t)(lowK >> 128), k7 = M::M7 * K;
-  Fe r;
-  asm("add.cc.u32  %0, %8,  %16;\n\t"
-      "addc.cc.u32 %1, %9,  %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, 0;\n\t"
-      "addc.cc.u32 %6, %14, 0;\n\t"
-      "addc.u32    %7, %15, %21;\n\t"
-      "sub.cc.u32  %0, %0, %22;\n\t"
-      "subc.cc.u32 %1, %1, %23;\n\t"
-      "subc.cc.u32 %2, %2, %24;\n\t"
-      "subc.cc.u32 %3, %3, %25;\n\t"
-      "subc.cc.u32 %4, %4, %26;\n\t"
-      "subc.cc.u32 %5, %5, %27;\n\t"
-      "subc.cc.u32 %6, %6, %28;\n\t"
-      "subc.u32    %7, %7, %29;\n\t"
-      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
-      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
-        "r"(k0), "r"(k1), "r"(k2), "r"(k3), "r"(k4), "r"(k7),
-        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
-  return r;
-}
 __device__ __noinline__ Fe quad_double(Fe c, int q, int qbase) {
   typedef ModP M;
   // stage 1: X^2, Y^2, Z^2 on lanes 0..2 and T Z (= X Y, so E = 2 T Z) on lane 3
@@ -627,22 +646,6 @@ __device__ __noinline__ Fe quad_double(Fe c, int q, int qbase) {
   Fe zero{{0, 0, 0, 0, 0, 0, 0, 0}};
   Fe H = fe_sub_lazy<1>(zero, ApB);            // m - (A + B)    in (0, m]
   return quad_stage2(E, F, G, H, q);
-}
-// a + b without the conditional subtraction (a, b < m: the sum is < 2m < 2^254)
-__device__ __forceinline__ Fe fe_add_lazy(const Fe& a, const Fe& b) {
-  Fe r;
-  asm("add.cc.u32  %0, %8,  %16;\n\t"
-      "addc.cc.u32 %1, %9,  %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, %21;\n\t"
-      "addc.cc.u32 %6, %14, %22;\n\t"
-      "addc.u32    %7, %15, %23;\n\t"
-      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
-      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
-        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
-  return r;
 }
 // c (distributed over the quad) += the full point p (every lane holds all of p; both canonical).  All linear combinations
 // are lazy (< 2m, see above) and computed by every lane before the select: a quad's lanes never branch apart except for
