@@ -979,8 +979,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     const int nwb = use_fb ? 1 : nwl;                           // bucket sets
     wmap.merged = use_fb ? 1 : 0;
     const size_t fb_entries = (size_t)nwl * n;
-    static const int fb_seg_env = getenv("ZC_FB_SEG") ? atoi(getenv("ZC_FB_SEG")) : 0;
-    const int fb_seg = fb_seg_env ? fb_seg_env : (fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8));
+    const int fb_seg = fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8);
     // workspace layout
     size_t o = 0;
     size_t o_cached = o; o = align_up(o + (use_fb ? 0 : n * 128), 256);

@@ -540,6 +540,15 @@ def test_msm_fixed_base_tables(zc, oracle):
         ctx.sync()
         w = want[0] if m == n else oracle.msm_naive(P[:m], svecs[0][:m], threads=8)
         assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), w), (c, m)
+    # tiny and ragged sizes through the merged bucket set
+    for m, c, R in ((1, 16, 1), (2, 8, 1), (33, 16, 2), (257, 10, 1), (1000, 16, 8)):
+        parts = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
+        for r in range(R):
+            ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), m, c, r, R))
+            ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), m, c, r, R, parts[r].data_ptr()))
+        ctx.check(L.zc_point_fold_dev(ctx._h, parts.data_ptr(), R, out.data_ptr()))
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P[:m], svecs[0][:m], threads=8)), (m, c, R)
     assert L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 17, 0, 1) == 3
     assert L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 16, 2, 2) == 2
     ctx.check(L.zc_msm_forget_points(ctx._h))
