@@ -81,3 +81,29 @@ def test_bytes_roundtrip_matches_oracle(oracle):
         fe = zc.FieldElement.from_bytes(b)
         assert np.array_equal(fe.limbs, oracle.fe_from_bytes(bytes(b)))
         assert fe.to_bytes() == oracle.fe_to_bytes(fe.limbs) == bytes(b)
+
+
+def test_ctypes_binding_matches_header_prototypes(so):
+    """Every int32_t-returning prototype in the header has ctypes argtypes of the same arity in _lib.py (ABI drift guard:
+    a missing or mis-sized argtypes entry silently truncates 64-bit arguments)."""
+    import re
+    with open(os.path.join(os.path.dirname(_lib.SO_PATH), "..", "include", "zerocaf_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    protos = re.findall(r"int32_t\s+(zc_\w+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) >= 90
+    L = _lib.lib()
+    bad = []
+    for name, args in protos:
+        n_args = 0 if args.strip() in ("", "void") else len(args.split(","))
+        at = getattr(getattr(L, name), "argtypes", None)
+        if at is None or len(at) != n_args:
+            bad.append((name, n_args, None if at is None else len(at)))
+    assert bad == []
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary header compiles as C99 (what a cgo / Rust bindgen / JNI consumer would feed it to)."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "zerocaf_b200.h"\nint main(void) { return (int)sizeof(zc_ctx *) * 0; }\n')
+    inc = os.path.join(os.path.dirname(_lib.SO_PATH), "..", "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
