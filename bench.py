@@ -351,6 +351,19 @@ def run_b200(args):
             ctx.check(L.zc_ristretto_eq_batch_dev(ctx._h, both.data_ptr(), ref2.data_ptr(), eq.data_ptr(), 2))
             ctx.sync()
             same_elem = bool(eq.all().item())
+        # second figure: the scalars are new for every MSM and live on rank 0 -- one NCCL broadcast of the
+        # 40 MiB limb array (32 MiB of information) in front of every call, on the MSM's stream
+        ms_msm_bcast = None
+        if world > 1:
+            try:
+                def msm_bcast_fn():
+                    with torch.cuda.stream(stream):
+                        dist.broadcast(S, src=0)
+                    msm_fn()
+                ms_msm_bcast, _ = timed(msm_bcast_fn, km, 2)
+            except Exception as e:                              # never let the secondary figure take the bench line down
+                print(f"[bench] scalar-broadcast figure skipped: {e}", file=sys.stderr)
+                ms_msm_bcast = None
         # fixed generators, memory traded for time: pre-scaled per-window tables (zc_msm_prepare_fixed_base_dev) -> one
         # merged bucket set per rank and no doubling chain
         t0 = time.perf_counter()
@@ -384,6 +397,7 @@ def run_b200(args):
             "all_ranks_identical_bits": identical, "matches_single_gpu_and_nccl_path": same_elem,
             "exchange": "NVLink peer-memory mailboxes: peer stores + flags + tree fold in one kernel" if world > 1 else None,
             "ms_per_msm_nccl_exchange": (ms_msm_nccl / 5) if world > 1 else None,
+            "ms_per_msm_incl_scalar_broadcast": (ms_msm_bcast / km) if ms_msm_bcast else None,
             "sharding": "bucket-window (w mod N), one exchange of the 160-B partial points + fixed-order fold" if world > 1 else "single GPU",
             "hbm_frac": 160.0 * N_MSM / (ms_msm / km * 1e-3) / 1e9 / peak}
 

@@ -88,6 +88,13 @@ res["ms_plain"] = timed(fn, a.iters)
 ctx.check(L.zc_msm_prepare_points_dev(ctx._h, P.data_ptr(), n))
 res["ms_prepared_points"] = timed(fn, a.iters)
 prepared_pt = out.clone()
+if world > 1:
+    # new scalars for every MSM, resident on rank 0: one NCCL broadcast of the limb array in front of every call
+    def fn_bcast():
+        with torch.cuda.stream(st):
+            dist.broadcast(S, src=0)
+        fn()
+    res["ms_prepared_points_incl_scalar_broadcast"] = timed(fn_bcast, a.iters, warmup=2)
 ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, P.data_ptr(), n, c, rank, world))
 res["ms_fixed_base_tables"] = timed(fn, a.iters)
 fb_pt = out.clone()
