@@ -45,3 +45,46 @@ def signed_digits(scalar_int, window_bits):
 
 def limbs_to_int(limbs):
     return sum(int(x) << (52 * i) for i, x in enumerate(np.asarray(limbs).reshape(-1)[:5]))
+
+
+# ---- the same digits without a carry chain, and the short-window rules (csrc/zc_msm.cu) -------------------------------
+SCALAR_BITS = 250            # canonical scalars are < L < 2^250
+
+
+def offset_digits(scalar_int, window_bits):
+    """msm_digits_kernel's recoding: with H = sum_w 2^(c-1) 2^(c w),  d_w = ((s + H) >> c w) mod 2^c - 2^(c-1).
+    Identical to signed_digits() for every canonical scalar."""
+    c = window_bits
+    nwin = num_windows(c)
+    H = sum(1 << (c - 1 + c * w) for w in range(nwin))
+    v = scalar_int + H
+    return [((v >> (c * w)) & ((1 << c) - 1)) - (1 << (c - 1)) for w in range(nwin)]
+
+
+def short_window_sub_bits(window_bits, w):
+    """A window that starts at bit c w >= 250 - (c-1) only sees digits in [0, 2^(250 - c w)]: the plain path spreads each of
+    its digits over 2^SUB sub-buckets chosen by the point index."""
+    ba = max(0, SCALAR_BITS - window_bits * w)
+    return (window_bits - 1) - ba if ba < window_bits - 1 else 0
+
+
+def merged_spread_bits(window_bits, w):
+    """Fixed-base (merged bucket set) path: rows of a short window are scaled by 2^(c w - SM) and its digit becomes
+    d 2^SM + (i mod 2^SM)."""
+    sub = short_window_sub_bits(window_bits, w)
+    return sub - 1 if SCALAR_BITS - window_bits * w > 0 and sub > 1 else 0
+
+
+def spread_digit(d, point_index, sm):
+    """The entry weight of point i in a spread short window (>= 0 for canonical scalars)."""
+    return d * (1 << sm) + (point_index & ((1 << sm) - 1))
+
+
+def fixed_base_table_rows(window_bits, rank, nranks, n):
+    """Rows (128 bytes each) of the tables zc_msm_prepare_fixed_base_dev builds on a rank."""
+    return len(windows_of_rank(window_bits, rank, nranks)) * n
+
+
+def fixed_base_row_shift(window_bits, w):
+    """A table row of window w is 2^shift * P_i."""
+    return window_bits * w - merged_spread_bits(window_bits, w)
