@@ -25,6 +25,7 @@
 
 #include "zc_internal.h"
 #include "zc_point.cuh"
+#include "zc_quad.cuh"
 
 using namespace zc;
 
@@ -35,82 +36,9 @@ namespace {
 constexpr int MAX_WINDOWS = 32;      // ceil(256 / 8)
 constexpr int MAX_GROUPS = 4;        // window groups processed top-down; the scaling chain of one group overlaps the next
 
-__device__ __forceinline__ void ld_fe(const uint32_t* __restrict__ p, Fe& a) {
-  uint4 lo = *reinterpret_cast<const uint4*>(p);
-  uint4 hi = *reinterpret_cast<const uint4*>(p + 4);
-  a.w[0] = lo.x; a.w[1] = lo.y; a.w[2] = lo.z; a.w[3] = lo.w;
-  a.w[4] = hi.x; a.w[5] = hi.y; a.w[6] = hi.z; a.w[7] = hi.w;
-}
-__device__ __forceinline__ void st_fe(uint32_t* __restrict__ p, const Fe& a) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(a.w[0], a.w[1], a.w[2], a.w[3]);
-  *reinterpret_cast<uint4*>(p + 4) = make_uint4(a.w[4], a.w[5], a.w[6], a.w[7]);
-}
-__device__ __forceinline__ Pt ld_pt(const uint32_t* __restrict__ p) {
-  Pt r; ld_fe(p, r.X); ld_fe(p + 8, r.Y); ld_fe(p + 16, r.Z); ld_fe(p + 24, r.T); return r;
-}
-__device__ __forceinline__ void st_pt(uint32_t* __restrict__ p, const Pt& a) {
-  st_fe(p, a.X); st_fe(p + 8, a.Y); st_fe(p + 16, a.Z); st_fe(p + 24, a.T);
-}
 // 1/d * R mod p: recovers 2T from the cached 2dT when a bucket is initialised from its first point
 __device__ __forceinline__ Fe DINV_MONT() {
   return Fe{{0x69c50bb0u, 0xa53327e2u, 0x96b47422u, 0xeaa0ffd5u, 0xfd35fb8fu, 0xd34f1e03u, 0x8d35344bu, 0x0b7245f4u}};
-}
-// lazy linear combinations (bucket accumulation, window chain, reduction trees): no conditional subtraction, results < 4m (inputs canonical);
-// mont_mul accepts them because the product of any two stays below R m = 2^256 m (16 m^2 > 8 m^2).
-__device__ __forceinline__ Fe fe_dbl_lazy(const Fe& a) {                 // 2a < 2m
-  Fe r;
-#pragma unroll
-  for (int k = 7; k > 0; k--) r.w[k] = __funnelshift_l(a.w[k - 1], a.w[k], 1);
-  r.w[0] = a.w[0] << 1;
-  return r;
-}
-// a - b + K m  (K = 1 or 2), a < K' m, b < K m
-template <int K>
-__device__ __forceinline__ Fe fe_sub_lazy(const Fe& a, const Fe& b) {
-  typedef ModP M;
-  constexpr uint64_t m01 = ((uint64_t)M::M1 << 32 | M::M0), m23 = ((uint64_t)M::M3 << 32 | M::M2);
-  // K * m as words (K <= 2: no overflow of the 4 low words into word 4 beyond a carry)
-  constexpr unsigned __int128 lowK = ((unsigned __int128)m23 << 64 | m01) * K;
-  constexpr uint32_t k0 = (uint32_t)lowK, k1 = (uint32_t)(lowK >> 32), k2 = (uint32_t)(lowK >> 64), k3 = (uint32_t)(lowK >> 96),
-                     k4 = (uint32_t)(lowK >> 128), k7 = M::M7 * K;
-  Fe r;
-  asm("add.cc.u32  %0, %8,  %16;\n\t"
-      "addc.cc.u32 %1, %9,  %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, 0;\n\t"
-      "addc.cc.u32 %6, %14, 0;\n\t"
-      "addc.u32    %7, %15, %21;\n\t"
-      "sub.cc.u32  %0, %0, %22;\n\t"
-      "subc.cc.u32 %1, %1, %23;\n\t"
-      "subc.cc.u32 %2, %2, %24;\n\t"
-      "subc.cc.u32 %3, %3, %25;\n\t"
-      "subc.cc.u32 %4, %4, %26;\n\t"
-      "subc.cc.u32 %5, %5, %27;\n\t"
-      "subc.cc.u32 %6, %6, %28;\n\t"
-      "subc.u32    %7, %7, %29;\n\t"
-      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
-      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
-        "r"(k0), "r"(k1), "r"(k2), "r"(k3), "r"(k4), "r"(k7),
-        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
-  return r;
-}
-// a + b without the conditional subtraction (a, b < m: the sum is < 2m < 2^254)
-__device__ __forceinline__ Fe fe_add_lazy(const Fe& a, const Fe& b) {
-  Fe r;
-  asm("add.cc.u32  %0, %8,  %16;\n\t"
-      "addc.cc.u32 %1, %9,  %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, %21;\n\t"
-      "addc.cc.u32 %6, %14, %22;\n\t"
-      "addc.u32    %7, %15, %23;\n\t"
-      : "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3]), "=&r"(r.w[4]), "=&r"(r.w[5]), "=&r"(r.w[6]), "=&r"(r.w[7])
-      : "r"(a.w[0]), "r"(a.w[1]), "r"(a.w[2]), "r"(a.w[3]), "r"(a.w[4]), "r"(a.w[5]), "r"(a.w[6]), "r"(a.w[7]),
-        "r"(b.w[0]), "r"(b.w[1]), "r"(b.w[2]), "r"(b.w[3]), "r"(b.w[4]), "r"(b.w[5]), "r"(b.w[6]), "r"(b.w[7]));
-  return r;
 }
 // ---- prep ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msm_prep_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
@@ -572,13 +500,6 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restri
   }
 }
 
-// lane-to-lane copies of a field element / point
-__device__ __forceinline__ Fe shfl_fe(const Fe& a, int src) {
-  Fe r;
-#pragma unroll
-  for (int k = 0; k < 8; k++) r.w[k] = __shfl_sync(0xffffffffu, a.w[k], src);
-  return r;
-}
 __device__ __forceinline__ Pt shfl_down_pt(const Pt& v, int d) {
   Pt o;
 #pragma unroll
@@ -614,65 +535,6 @@ __global__ void __launch_bounds__(256) msm_unfold_kernel(const uint32_t* __restr
   Pt p = k < nreal ? ld_pt(folded + 32 * (size_t)k) : pt_identity_mont();
   st_pt(buckets + 32 * (size_t)k, p);
 }
-
-// ---- four lanes per point operation (window chain and the latency-bound reduction kernels) ---------------------------
-// Lane q = lane & 3 holds coordinate q (X, Y, Z, T) of the running point; the four independent field multiplications
-// of each of the two stages of a doubling / addition run on the four lanes, the operands travel by shuffle.  This
-// turns the strictly serial tail (c doublings per window) from ~8 dependent multiplications per operation into 2.
-__device__ __forceinline__ Fe quad_stage2(const Fe& E, const Fe& F, const Fe& G, const Fe& H, int q) {
-  typedef ModP M;
-  // X3 = E F, Y3 = G H, Z3 = F G, T3 = E H
-  Fe u, v;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    u.w[k] = (q == 0 || q == 3) ? E.w[k] : (q == 1 ? G.w[k] : F.w[k]);
-    v.w[k] = (q == 0) ? F.w[k] : (q == 2 ? G.w[k] : H.w[k]);
-  }
-  return mont_mul<M>(u, v);
-}
-__device__ __noinline__ Fe quad_double(Fe c, int q, int qbase) {
-  typedef ModP M;
-  // stage 1: X^2, Y^2, Z^2 on lanes 0..2 and T Z (= X Y, so E = 2 T Z) on lane 3
-  Fe z = shfl_fe(c, qbase + 2);
-  Fe in2 = c;
-  if (q == 3) in2 = z;
-  Fe s = mont_mul<M>(c, in2);
-  Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), ZZ = shfl_fe(s, qbase + 2), TZ = shfl_fe(s, qbase + 3);
-  Fe E = fe_dbl_lazy(TZ);                      // < 2m
-  Fe C = fe_dbl_lazy(ZZ);                      // < 2m
-  Fe G = fe_sub_lazy<1>(B, A);                 // B - A + m      in (0, 2m)
-  Fe F = fe_sub_lazy<2>(G, C);                 // G - C + 2m     in (0, 4m)
-  Fe ApB = fe_add<M>(A, B);                    // canonical
-  Fe zero{{0, 0, 0, 0, 0, 0, 0, 0}};
-  Fe H = fe_sub_lazy<1>(zero, ApB);            // m - (A + B)    in (0, m]
-  return quad_stage2(E, F, G, H, q);
-}
-// c (distributed over the quad) += the full point p (every lane holds all of p; both canonical).  All linear combinations
-// are lazy (< 2m, see above) and computed by every lane before the select: a quad's lanes never branch apart except for
-// lane 3's 2d T2 product.
-__device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) {
-  typedef ModP M;
-  const Fe x1 = shfl_fe(c, qbase), y1 = shfl_fe(c, qbase + 1);
-  const Fe d1 = fe_sub_lazy<1>(y1, x1), s1 = fe_add_lazy(y1, x1);
-  const Fe d2 = fe_sub_lazy<1>(p.Y, p.X), s2 = fe_add_lazy(p.Y, p.X);
-  const Fe z2 = fe_dbl_lazy(p.Z);
-  Fe t2 = p.T;
-  if (q == 3) t2 = mont_mul<M>(p.T, D2_MONT());
-  Fe u, v;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    u.w[k] = q == 0 ? d1.w[k] : (q == 1 ? s1.w[k] : c.w[k]);
-    v.w[k] = q == 0 ? d2.w[k] : (q == 1 ? s2.w[k] : (q == 2 ? z2.w[k] : t2.w[k]));
-  }
-  const Fe s = mont_mul<M>(u, v);                              // A, B, D = 2 Z1 Z2, C = T1 2d T2
-  const Fe A = shfl_fe(s, qbase), B = shfl_fe(s, qbase + 1), D = shfl_fe(s, qbase + 2), C = shfl_fe(s, qbase + 3);
-  const Fe E = fe_sub_lazy<1>(B, A);
-  const Fe F = fe_sub_lazy<1>(D, C);
-  const Fe G = fe_add_lazy(D, C);
-  const Fe H = fe_add_lazy(B, A);
-  return quad_stage2(E, F, G, H, q);
-}
-
 
 // ---- bucket reduction  W = sum_k (k+1) B_k  by digit marginals ("cube" reduction) ----------------------------------
 // Write the bucket index as four digits  k = k3 2^(A0+a1+a2) + k2 2^(A0+a1) + k1 2^A0 + k0  (k0: lane, k1: warp in
@@ -920,6 +782,7 @@ __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restric
   for (int j = 0; j < gap_post; j++) c = quad_double(c, q, qbase);
   // fixed-base spread correction (ABI layout): normal-form words are a Montgomery-form representative of the same point
   if (corr52) c = quad_add(c, pt_load52(corr52), q, qbase);
+  c = fe_canon4(c);                                // the quad operations leave coordinates lazily reduced (< 2.5 m)
   Pt r;
   r.X = shfl_fe(c, 0); r.Y = shfl_fe(c, 1); r.Z = shfl_fe(c, 2); r.T = shfl_fe(c, 3);
   if (lane == 0) {
