@@ -68,6 +68,7 @@ struct zc_ctx {
   uint64_t msm_graph_launches = 0;
   // MSM: side stream for the window-scaling chain + events (created on first use)
   cudaStream_t side_stream = nullptr, side_extra[3] = {nullptr, nullptr, nullptr}, chain_stream = nullptr, sort_stream = nullptr;
+  cudaStream_t side_hi[3] = {nullptr, nullptr, nullptr};   // high-priority twins of the first three side streams (sharded MSM)
   cudaEvent_t ev[16] = {};
 };
 

@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
 // Buckets with at most FIX_INLINE partials are stitched on the fly by whoever reads them (load_bucket, used by the
 // first reduction stage); heavier ones are queued here for msm_heavy_kernel (one warp per bucket, tree sum), which
 // writes them into buckets[].
-constexpr int FIX_INLINE = 6;       // per-window buckets; the merged buckets of the fixed-base path choose theirs per call
+static const int FIX_INLINE = getenv("ZC_MSM_FIX_INLINE") ? atoi(getenv("ZC_MSM_FIX_INLINE")) : 6;       // per-window buckets; the merged buckets of the fixed-base path choose theirs per call
 __global__ void __launch_bounds__(256) msm_fixq_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
                                                        int seg, int nwl, int nb, int fix_inline, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
   size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -705,6 +705,40 @@ __global__ void __launch_bounds__(128) msm_stitch_kernel(BucketSrc src, uint32_t
   if (s_first == s_last || s_last - s_first + 1 > (uint32_t)src.fix_inline) return;     // already final
   st_pt(buckets + 32 * g, load_bucket(src, g));
 }
+// The same pass with four lanes per bucket (one quad stitches one bucket, 32 buckets per block): a stitch is a handful of
+// dependent additions, two multiplication latencies each on a quad instead of nine in one thread, and a lane holds one
+// coordinate + the operand, so the blocks are light enough to run beside the next window's accumulation (whose CTAs
+// leave ~24 K registers free on half of the SMs; the one-lane kernel's 256 blocks went through those slots in three
+// waves: 97 us against 25 us alone).  The loop runs to the longest stitch of the warp (the shuffles need all lanes).
+__global__ void __launch_bounds__(128) msm_stitch_quad_kernel(BucketSrc src, uint32_t* __restrict__ buckets, size_t total) {
+  const int q = threadIdx.x & 3, qbase = threadIdx.x & 28;
+  const size_t g = (size_t)blockIdx.x * 32 + (threadIdx.x >> 2);
+  const bool valid = g < total;
+  const uint32_t cnt = valid ? src.hist[g] : 0u;
+  const uint32_t o = valid ? src.offs[g] : 0u, e = o + cnt;
+  const uint32_t s_first = o / (uint32_t)src.seg, s_last = cnt ? (e - 1) / (uint32_t)src.seg : s_first;
+  const size_t wl = valid ? g / src.nb : 0;
+  const uint32_t* H = src.partH + 32 * (wl * src.nseg);
+  const uint32_t* T = src.partT + 32 * (wl * src.nseg);
+  int np = 0;                                                       // partials to add to the first one
+  bool write = valid && cnt == 0;                                   // empty bucket: the identity
+  Fe acc = identity_coord(q);
+  if (valid && cnt != 0 && s_first != s_last && s_last - s_first + 1 <= (uint32_t)src.fix_inline) {
+    np = (int)(s_last - s_first);
+    write = true;
+    acc = ld_coord((o == s_first * (uint32_t)src.seg ? H : T) + 32 * (size_t)s_first, q);
+  }
+  int mx = np;
+#pragma unroll
+  for (int d = 16; d >= 4; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+#pragma unroll 1
+  for (int k = 1; k <= mx; k++) {
+    const bool on = k <= np;
+    const Fe r = quad_add(acc, ld_pt(H + 32 * (size_t)(on ? s_first + k : 0)), q, qbase);
+    if (on) acc = r;
+  }
+  if (write) st_coord(buckets + 32 * g, q, fe_canon4(acc));          // canonical: load_bucket / msm_fold_kernel read these too
+}
 // stage 1 with four lanes per point (fixed-base path: one bucket set, nothing else on the GPU at that point; the trees
 // are depth-bound).  One block of 64 quads per 128 final buckets (k1 = row 0..3, k0 = column 0..31).  Every quad starts
 // in a row tree (16 quads per row); the quads that drop out of it first take the 32 column sums while quad 0 adds up
@@ -912,6 +946,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_lo));
       for (int i = 0; i < 2; i++) ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_extra[i], cudaStreamNonBlocking, prio_lo));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_extra[2], cudaStreamNonBlocking, prio_hi));
+      for (int i = 0; i < 3; i++) ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_hi[i], cudaStreamNonBlocking, prio_hi));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, prio_hi));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sort_stream, cudaStreamNonBlocking, prio_lo));
       for (int i = 0; i < 16; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
@@ -920,7 +955,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     // the groups' reductions are independent and latency-bound, so they get their own streams and overlap.  chain: the
     // serial window chain.  Events: ev[0] fork, ev[1] prep done, ev[2+g] group g accumulated, ev[6+g] group g reduced,
     // ev[10] chain done.
-    cudaStream_t sides[4] = {ctx->side_stream, ctx->side_extra[0], ctx->side_extra[1], ctx->side_extra[2]};
+    // One GPU: the early groups' reductions have slack (low priority: they must not take SMs from the accumulation that
+    // follows).  Sharded: a rank owns few windows and every reduction feeds the serial window chain -- all high priority.
+    static const bool stitch_quad = !(getenv("ZC_MSM_STITCH_QUAD") && atoi(getenv("ZC_MSM_STITCH_QUAD")) == 0);
+    static const int hi_prio_env = getenv("ZC_MSM_HI_PRIO") ? atoi(getenv("ZC_MSM_HI_PRIO")) : -1;
+    const bool hi_prio = hi_prio_env >= 0 ? hi_prio_env != 0 : nranks > 1;
+    cudaStream_t sides[4] = {hi_prio ? ctx->side_hi[0] : ctx->side_stream, hi_prio ? ctx->side_hi[1] : ctx->side_extra[0],
+                             hi_prio ? ctx->side_hi[2] : ctx->side_extra[1], ctx->side_extra[2]};
     cudaStream_t side = sides[0], chain = ctx->chain_stream;
 
     // The ~25 launches and the two-stream fork/join of one MSM are recorded once into a CUDA graph and replayed while
@@ -1016,7 +1057,8 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         msm_fixq_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(offs, hist, seg, 1, nb, fix_inline, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_fixq_kernel");
         msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_heavy_kernel");
         const BucketSrc src = {offs, hist, partH, partT, buckets, nseg, nb, seg, fix_inline};
-        msm_stitch_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(src, buckets, (size_t)nb); nlaunch++; mark(st, 0, "msm_stitch_kernel");
+        if (stitch_quad) { msm_stitch_quad_kernel<<<(unsigned)((nb + 31) / 32), 128, 0, st>>>(src, buckets, (size_t)nb); nlaunch++; mark(st, 0, "msm_stitch_quad_kernel"); }
+        else { msm_stitch_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(src, buckets, (size_t)nb); nlaunch++; mark(st, 0, "msm_stitch_kernel"); }
         msm_cube1_quad_kernel<<<(unsigned)nblk, 256, 0, st>>>(buckets, btot, pm1, pm0); nlaunch++; mark(st, 0, "msm_cube1_quad_kernel");
         msm_cube2a_kernel<<<(unsigned)ntask, 4 * C2A_QUADS, 0, st>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(st, 0, "msm_cube2a_kernel");
         msm_cube2b_kernel<<<4, 128, 0, st>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(st, 0, "msm_cube2b_kernel");
@@ -1050,10 +1092,21 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         nlaunch++; mark(st, 0, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
-        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
-        ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
-        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, side>>>(g_offs, g_hist, seg, gsz, nb, FIX_INLINE, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_fixq_kernel");
-        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, side>>>(g_offs, g_hist, nseg, seg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++; mark(side, 1, "msm_heavy_kernel");
+        // Stage 1 of a reduction (stitch + the first trees) is wide: beside the next group's accumulation it competes for the
+        // multiplier pipe and takes 4-5x longer (97 + 45 us instead of 21 + 25 us for one window of 2^15 buckets).  On one
+        // GPU that is hidden; sharded, the first group's reduction feeds a long window chain, so when that chain is long
+        // stage 1 runs ON the main stream, ahead of the next accumulation.  ZC_MSM_SEQ_STAGE1 = 0 / 1 forces it.
+        static const int seq_env = getenv("ZC_MSM_SEQ_STAGE1") ? atoi(getenv("ZC_MSM_SEQ_STAGE1")) : -1;
+        const int chain_after = (g == ngroups - 1) ? 0 : c * (tasks[lo].w - tasks[lo - 1].w);   // doublings this group's sums wait for
+        const bool seq1 = (g < ngroups - 1) && (seq_env >= 0 ? seq_env != 0 : (nranks > 1 && chain_after >= 96));
+        cudaStream_t s1 = seq1 ? st : side;
+        const int s1id = seq1 ? 0 : 1;
+        if (!seq1) {
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
+          ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
+        }
+        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s1>>>(g_offs, g_hist, seg, gsz, nb, FIX_INLINE, g_hcount, g_hlist); nlaunch++; mark(s1, s1id, "msm_fixq_kernel");
+        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, s1>>>(g_offs, g_hist, nseg, seg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++; mark(s1, s1id, "msm_heavy_kernel");
         const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb, seg, FIX_INLINE};
         // A short (top) window spreads each digit over 2^sub sub-buckets.  sub == A0: the sub-bucket index is exactly the
         // lane digit of the cube, which then simply carries weight 0 (drop).  Otherwise sum the sub-buckets back first.
@@ -1064,23 +1117,28 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         // reductions share the SMs with the next group's accumulation, so their total SM time matters, not only their depth.
         static const int quad_stage1_env = getenv("ZC_MSM_QUAD_STAGE1") ? atoi(getenv("ZC_MSM_QUAD_STAGE1")) : 1;
         const bool quad_stage1 = quad_stage1_env == 1 || (quad_stage1_env == 2 && g == ngroups - 1);
-        if (quad_stage1) { msm_stitch_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, side>>>(src, g_buckets, tot); nlaunch++; mark(side, 1, "msm_stitch_kernel"); }
+        if (quad_stage1 && stitch_quad) { msm_stitch_quad_kernel<<<(unsigned)((tot + 31) / 32), 128, 0, s1>>>(src, g_buckets, tot); nlaunch++; mark(s1, s1id, "msm_stitch_quad_kernel"); }
+        else if (quad_stage1) { msm_stitch_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, s1>>>(src, g_buckets, tot); nlaunch++; mark(s1, s1id, "msm_stitch_kernel"); }
         for (int wl = lo; wl < hi; wl++) {
           const int sub = short_window_sub_bits(c, tasks[wl].w);
           if (sub == A0 && g == 0 && wl == hi - 1) drop_wl = wl - lo;
           else if (sub > 0) {
             raw_mask |= 1u << (wl - lo);
-            msm_fold_kernel<<<(unsigned)(((nb >> sub) + 3) / 4), 128, 0, side>>>(src, (size_t)(wl - lo), sub, folded + (size_t)(g == ngroups - 1 ? 3 : g % 3) * nb * 32); nlaunch++; mark(side, 1, "msm_fold_kernel");
-            msm_unfold_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, side>>>(folded + (size_t)(g == ngroups - 1 ? 3 : g % 3) * nb * 32, nb, nb >> sub, buckets + 32 * ((size_t)wl * nb)); nlaunch++; mark(side, 1, "msm_unfold_kernel");
+            msm_fold_kernel<<<(unsigned)(((nb >> sub) + 3) / 4), 128, 0, s1>>>(src, (size_t)(wl - lo), sub, folded + (size_t)(g == ngroups - 1 ? 3 : g % 3) * nb * 32); nlaunch++; mark(s1, s1id, "msm_fold_kernel");
+            msm_unfold_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s1>>>(folded + (size_t)(g == ngroups - 1 ? 3 : g % 3) * nb * 32, nb, nb >> sub, buckets + 32 * ((size_t)wl * nb)); nlaunch++; mark(s1, s1id, "msm_unfold_kernel");
           }
         }
         const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
         if (quad_stage1) {
-          msm_cube1_quad_kernel<<<(unsigned)((size_t)gsz * nblk), 256, 0, side>>>(g_buckets, btot + 32 * ((size_t)lo * nblk),
-              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(side, 1, "msm_cube1_quad_kernel");
+          msm_cube1_quad_kernel<<<(unsigned)((size_t)gsz * nblk), 256, 0, s1>>>(g_buckets, btot + 32 * ((size_t)lo * nblk),
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(s1, s1id, "msm_cube1_quad_kernel");
         } else {
-          msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, side>>>(src, raw_mask, a1, btot + 32 * ((size_t)lo * nblk),
-              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(side, 1, "msm_cube1_kernel");
+          msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, s1>>>(src, raw_mask, a1, btot + 32 * ((size_t)lo * nblk),
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(s1, s1id, "msm_cube1_kernel");
+        }
+        if (seq1) {
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
+          ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
         }
         msm_cube2a_kernel<<<(unsigned)((size_t)gsz * ntask), 4 * C2A_QUADS, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
             pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz,
