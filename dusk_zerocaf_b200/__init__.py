@@ -5,9 +5,9 @@ RistrettoPoint with Add/Sub/Mul/Neg/Identity/Double/Square) plus the batch API; 
 CUDA kernels behind the C ABI of libzerocaf_b200.so (include/zerocaf_b200.h).  There is no CPU fallback.
 """
 from ._lib import ZerocafError, SO_PATH, header_symbols, build, lib   # noqa: F401
-from .context import Context, default_context   # noqa: F401
+from .context import Context, Generators, default_context, GEN_PREPARED, GEN_FIXED_BASE   # noqa: F401
 from .types import FieldElement, Scalar, EdwardsPoint, RistrettoPoint   # noqa: F401
-from . import batch   # noqa: F401
+from . import batch, synth   # noqa: F401
 
 SCALAR_MUL_STRICT = 0
 SCALAR_MUL_FAST = 1

@@ -93,15 +93,29 @@ def lib():
         getattr(L, "zc_scalar_window_naf_batch" + suf).argtypes = [vp, vp, i32, vp, sz]
         getattr(L, "zc_fe_sqrt_ratio_i_batch" + suf).argtypes = [vp, vp, vp, vp, vp, sz]
     L.zc_msm_sharded_dev.argtypes = [vp, vp, vp, sz, i32, vp]
-    L.zc_msm_prepare_points_dev.argtypes = [vp, vp, sz]
-    L.zc_msm_forget_points.argtypes = [vp]
-    L.zc_msm_prepare_fixed_base_dev.argtypes = [vp, vp, sz, i32, i32, i32]
+    L.zc_msm_sharded.argtypes = [vp, vp, vp, sz, i32, vp]
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    for suf in ("", "_dev"):
+        getattr(L, "zc_fe_mul_square_batch_packed" + suf).argtypes = [vp, vp, vp, vp, vp, sz]
+        getattr(L, "zc_fe_div_batch" + suf).argtypes = [vp, vp, vp, vp, sz]
+        getattr(L, "zc_scalar_into_bits_batch" + suf).argtypes = [vp, vp, vp, sz]
+        for kind in ("fe", "scalar", "point"):
+            getattr(L, f"zc_{kind}_check_canonical_batch{suf}").argtypes = [vp, vp, sz, u64p]
+    L.zc_ctx_set_validation.argtypes = [vp, i32]
+    L.zc_msm_generators_create_dev.argtypes = [vp, vp, sz, i32, i32, i32, i32, ctypes.POINTER(vp)]
+    L.zc_msm_generators_destroy.argtypes = [vp, vp]
+    L.zc_msm_generators_info.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(i32), ctypes.POINTER(sz)]
+    L.zc_msm_gen_dev.argtypes = [vp, vp, vp, i32, vp]
+    L.zc_msm_gen_partial_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.zc_msm_gen_sharded_dev.argtypes = [vp, vp, vp, i32, vp]
     L.zc_msm_partial_dev.argtypes = [vp, vp, vp, sz, i32, i32, i32, vp]
     L.zc_point_fold_dev.argtypes = [vp, vp, sz, vp]
     L.zc_ctx_set_nccl.argtypes = [vp, vp, i32, i32]
     L.zc_nccl_unique_id.argtypes = [vp]
     L.zc_peer_mailbox_create.argtypes = [vp, vp]
     L.zc_peer_mailbox_connect.argtypes = [vp, vp, i32, i32]
+    L.zc_peer_mailbox_ptr.argtypes = [vp, ctypes.POINTER(vp)]
+    L.zc_peer_mailbox_connect_local.argtypes = [vp, ctypes.POINTER(vp), i32, i32]
     L.zc_nccl_comm_init.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.zc_nccl_comm_destroy.argtypes = [vp]
     _lib = L

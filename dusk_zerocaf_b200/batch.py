@@ -222,6 +222,47 @@ def fe_sqrt_ratio_i(u, v, ctx=None):
     return out, sq
 
 
+def fe_div(a, b, ctx=None):
+    """Div (field.rs:277-299): a * b^-1; a / 0 = 0 where the reference asserts."""
+    ctx = ctx or default_context()
+    a, b = _arr(a, 5), _arr(b, 5)
+    out = np.empty_like(a)
+    ctx.call("zc_fe_div_batch", a, b, out, a.shape[0])
+    return out
+
+
+def scalar_into_bits(a, ctx=None):
+    """Scalar::into_bits (scalar.rs:352-366): (n, 256) uint8, least significant bit first."""
+    ctx = ctx or default_context()
+    a = _arr(a, 5)
+    out = np.empty((a.shape[0], 256), dtype=np.uint8)
+    ctx.call("zc_scalar_into_bits_batch", a, out, a.shape[0])
+    return out
+
+
+def fe_mul_square_packed(a_bytes, b_bytes, ctx=None):
+    """Config 2 on the 32-byte wire format (to_bytes / from_bytes, field.rs:563-631): ((n, 32) prod, (n, 32) sq) uint8."""
+    ctx = ctx or default_context()
+    a = np.ascontiguousarray(a_bytes, dtype=np.uint8).reshape(-1, 32)
+    b = np.ascontiguousarray(b_bytes, dtype=np.uint8).reshape(-1, 32)
+    prod, sq = np.empty_like(a), np.empty_like(a)
+    ctx.call("zc_fe_mul_square_batch_packed", a, b, prod, sq, a.shape[0])
+    return prod, sq
+
+
+def check_canonical(kind, a, ctx=None):
+    """zc_{fe,scalar,point}_check_canonical_batch: None when every element is canonical, else the first offending index."""
+    import ctypes
+    ctx = ctx or default_context()
+    a = _arr(a, 20 if kind == "point" else 5)
+    bad = ctypes.c_uint64(0)
+    st = getattr(ctx._L, f"zc_{kind}_check_canonical_batch")(ctx._h, a.ctypes.data, a.shape[0], ctypes.byref(bad))
+    if st == 4:
+        return int(bad.value)
+    ctx.check(st)
+    return None
+
+
 def msm(points, scalars, window_bits=16, ctx=None):
     """sum_i [s_i] P_i as an EdwardsPoint (20 limbs); a group element, compare canonically."""
     ctx = ctx or default_context()

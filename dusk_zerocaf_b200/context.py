@@ -49,6 +49,11 @@ class Context:
     def sync(self):
         self.check(self._L.zc_ctx_sync(self._h))
 
+    def set_validation(self, on=True):
+        """zc_ctx_set_validation: the hot-path entry points check their inputs (limbs < 2^52, value < modulus) and return
+        ZC_ERR_NONCANONICAL (status 4) instead of a silently wrong result."""
+        self.check(self._L.zc_ctx_set_validation(self._h, 1 if on else 0))
+
     @property
     def launches(self):
         return int(self._L.zc_ctx_launch_count(self._h))
@@ -84,18 +89,69 @@ class Context:
         self.check(self._L.zc_peer_mailbox_connect(self._h, ctypes.cast(allb, ctypes.c_void_p), int(rank), int(nranks)))
 
 
+    @staticmethod
+    def connect_local(contexts):
+        """Several contexts of THIS process (several GPUs with peer access, or several streams of one GPU) as the ranks of
+        one sharded MSM: zc_peer_mailbox_ptr + zc_peer_mailbox_connect_local, rank = position in the list."""
+        n = len(contexts)
+        ptrs = (ctypes.c_void_p * n)()
+        for r, cx in enumerate(contexts):
+            scratch = (ctypes.c_uint8 * 64)()
+            cx.check(cx._L.zc_peer_mailbox_create(cx._h, ctypes.cast(scratch, ctypes.c_void_p)))
+            p = ctypes.c_void_p()
+            cx.check(cx._L.zc_peer_mailbox_ptr(cx._h, ctypes.byref(p)))
+            ptrs[r] = p.value
+        for r, cx in enumerate(contexts):
+            cx.check(cx._L.zc_peer_mailbox_connect_local(cx._h, ptrs, r, n))
+
     # ---- fixed generators --------------------------------------------------------------------------------------
-    def msm_prepare_points(self, points_dev_ptr, n):
-        """zc_msm_prepare_points_dev: cache the MSM operands of a resident point set (Z = 1, cached form)."""
-        self.check(self._L.zc_msm_prepare_points_dev(self._h, points_dev_ptr, int(n)))
+    def msm_generators(self, points_dev_ptr, n, kind=1, window_bits=16, rank=0, nranks=1):
+        """zc_msm_generators_create_dev: an opaque handle owning the prepared operands (kind 1, ZC_GEN_PREPARED) or the
+        pre-scaled fixed-base tables (kind 2, ZC_GEN_FIXED_BASE) of a resident point set.  The points are read during
+        creation only."""
+        return Generators(self, points_dev_ptr, n, kind, window_bits, rank, nranks)
 
-    def msm_prepare_fixed_base(self, points_dev_ptr, n, window_bits=16, rank=0, nranks=1):
-        """zc_msm_prepare_fixed_base_dev: pre-scaled rows 2^(c w) P_i for the windows rank owns (one merged bucket set and
-        no doubling chain in later MSM calls of this shape)."""
-        self.check(self._L.zc_msm_prepare_fixed_base_dev(self._h, points_dev_ptr, int(n), int(window_bits), int(rank), int(nranks)))
 
-    def msm_forget_points(self):
-        self.check(self._L.zc_msm_forget_points(self._h))
+GEN_PREPARED, GEN_FIXED_BASE = 1, 2
+
+
+class Generators:
+    """Handle of zc_msm_generators (include/zerocaf_b200.h): close() (or the owning context's close) releases it."""
+
+    def __init__(self, ctx, points_dev_ptr, n, kind, window_bits, rank, nranks):
+        self.ctx = ctx
+        h = ctypes.c_void_p()
+        ctx.check(ctx._L.zc_msm_generators_create_dev(ctx._h, points_dev_ptr, int(n), int(kind), int(window_bits), int(rank),
+                                                      int(nranks), ctypes.byref(h)))
+        self._g = h
+        self.n, self.kind, self.window_bits = int(n), int(kind), int(window_bits)
+
+    @property
+    def device_bytes(self):
+        b = ctypes.c_size_t()
+        self.ctx._L.zc_msm_generators_info(self._g, None, None, ctypes.byref(b))
+        return int(b.value)
+
+    def msm(self, scalars_dev_ptr, out_dev_ptr, window_bits=None):
+        self.ctx.check(self.ctx._L.zc_msm_gen_dev(self.ctx._h, self._g, scalars_dev_ptr, int(window_bits or self.window_bits), out_dev_ptr))
+
+    def msm_partial(self, scalars_dev_ptr, out_dev_ptr, rank, nranks, window_bits=None):
+        self.ctx.check(self.ctx._L.zc_msm_gen_partial_dev(self.ctx._h, self._g, scalars_dev_ptr, int(window_bits or self.window_bits),
+                                                          int(rank), int(nranks), out_dev_ptr))
+
+    def msm_sharded(self, scalars_dev_ptr, out_dev_ptr, window_bits=None):
+        self.ctx.check(self.ctx._L.zc_msm_gen_sharded_dev(self.ctx._h, self._g, scalars_dev_ptr, int(window_bits or self.window_bits), out_dev_ptr))
+
+    def close(self):
+        if getattr(self, "_g", None) and getattr(self.ctx, "_h", None):
+            self.ctx.check(self.ctx._L.zc_msm_generators_destroy(self.ctx._h, self._g))
+        self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default = None

@@ -94,6 +94,14 @@ __global__ void __launch_bounds__(TPB) fe_invert_kernel(const uint64_t* __restri
   fe_store52(out + 5 * i, from_mont<ModP>(fe_pow_const(x, E_INV, 253)));
 }
 
+// a / b = a * b^-1  (Div, field.rs:277-299; the reference asserts b != 0 -- here a / 0 = 0 like inverse(0))
+__global__ void __launch_bounds__(TPB) fe_div_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const Fe binv = fe_pow_const(to_mont<ModP>(fe_load52(b + 5 * i)), E_INV, 253);      // b^-1 R
+  fe_store52(out + 5 * i, mul_ni(fe_load52(a + 5 * i), binv));                          // normal * Montgomery -> normal
+}
+
 // (x, y) = (X / Z, Y / Z)                                                                        edwards.rs:1085-1092
 __global__ void __launch_bounds__(TPB) pt_to_affine_kernel(const uint64_t* __restrict__ p, uint64_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
@@ -308,6 +316,28 @@ int32_t zc_fe_invert_batch(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t
   return host_unary(ctx, a, n * 40, out, n * 40, [&](void* di, void* dout) {
     return zc_fe_invert_batch_dev(ctx, (const uint64_t*)di, (uint64_t*)dout, n);
   });
+}
+
+int32_t zc_fe_div_batch_dev(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, a && b && out);
+  fe_div_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(a, b, out, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_fe_div_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  ZC_ENC_PROLOGUE(ctx, n, a && b && out);
+  void *da = nullptr, *db = nullptr, *dout = nullptr;
+  int32_t rc;
+  if ((rc = zc_scratch(ctx, 0, n * 40, &da))) return rc;
+  if ((rc = zc_scratch(ctx, 1, n * 40, &db))) return rc;
+  if ((rc = zc_scratch(ctx, 2, n * 40, &dout))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(da, a, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  ZC_CUDA(ctx, cudaMemcpyAsync(db, b, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = zc_fe_div_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, n))) return rc;
+  ZC_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZC_OK;
 }
 
 int32_t zc_fe_sqrt_ratio_i_batch_dev(zc_ctx* ctx, const uint64_t* u, const uint64_t* v, uint64_t* out, uint8_t* was_square, size_t n) {

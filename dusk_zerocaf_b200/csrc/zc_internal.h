@@ -14,17 +14,29 @@
 struct zc_msm_key {
   const void *points, *scalars;
   size_t n;
-  int32_t c, rank, nranks, pad;
+  int32_t c, rank, nranks, mode;
   const void *partial, *ws;
+  uint64_t gens_id;                   // 0 = no generator handle
+};
+
+// Fixed generators prepared once (zc_msm_generators_create_dev).  The handle OWNS everything derived from the points -- the
+// caller's point array is not referenced after creation, so freeing, reusing or overwriting it cannot alias a later MSM.
+struct zc_msm_generators {
+  uint64_t id;                        // unique per creation (a recycled heap address never matches a recorded graph)
+  zc_ctx *owner;
+  int32_t kind, c, rank, nranks;      // c / rank / nranks: the call shape fixed-base tables were built for
+  size_t n;
+  void *cached;                       // n x 128 B affine cached operands (y+x, y-x, 1, 2dxy), Montgomery words
+  void *table;                        // ZC_GEN_FIXED_BASE: rows 2^(c w) P_i for the windows of (rank, nranks), same record
+  size_t table_bytes;
+  void *corr;                         // [u64;20]: minus the constant a spread short window adds (zc_msm.cu), or null
 };
 
 // NVLink peer-memory exchange (zc_peer.cu): one mailbox per rank, mapped into every peer with CUDA IPC
 #define ZC_MAX_PEERS 16
-struct zc_mailbox {
-  uint64_t flag[ZC_MAX_PEERS];        // flag[r] = sequence number of the last partial rank r delivered here
-  uint64_t counter;                   // this rank's own exchange count
-  uint64_t pad[15];
-  uint64_t slot[ZC_MAX_PEERS][20];    // slot[r] = rank r's partial point, [u64;20]
+struct zc_mailbox {                     // double-buffered by the parity of the exchange's sequence number
+  uint64_t flag[2][ZC_MAX_PEERS];     // flag[par][r] = sequence number of the last partial rank r delivered into slot[par][r]
+  uint64_t slot[2][ZC_MAX_PEERS][20]; // slot[par][r] = rank r's partial point, [u64;20]
 };
 struct zc_peer_ptrs { zc_mailbox* p[ZC_MAX_PEERS]; };
 
@@ -48,20 +60,19 @@ struct zc_ctx {
   void *mailbox = nullptr;      // zc_mailbox in this rank's HBM
   zc_peer_ptrs peers = {};
   bool peers_connected = false;
+  bool peers_ipc = false;             // peers.p[] were opened with cudaIpcOpenMemHandle (else plain pointers of this process)
+  uint64_t peer_seq = 0;              // exchanges started on this context (every rank counts the same calls, failed ones included)
+  void *peer_error_host = nullptr;    // mapped host word: (sequence << 8 | missing rank + 1) of a timed-out exchange
+  uint64_t *peer_error_dev = nullptr;
   // host-pointer entry points: copy-in / copy-out streams and per-chunk events (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t pipe_ev[2 * ZC_PIPE_MAX_CHUNKS] = {};
-  // MSM operands prepared once for fixed generators (zc_msm_prepare_points_dev)
-  const void *prep_points = nullptr;
-  size_t prep_n = 0;
-  bool prep_valid = false;
-  // fixed-base MSM tables (zc_msm_prepare_fixed_base_dev): 2^(c w) P_i for this rank's windows, affine cached form
-  void *fb_table = nullptr;
-  void *fb_corr = nullptr;          // [u64;20]: minus the constant a spread short window adds (zc_msm.cu), or null
-  size_t fb_table_bytes = 0;
-  const void *fb_points = nullptr;
-  size_t fb_n = 0;
-  int32_t fb_c = 0, fb_rank = 0, fb_nranks = 0;
+  // input validation (zc_ctx_set_validation): first offending element index, ~0 = none
+  bool validate = false, in_pipeline = false;
+  size_t vbase = 0;
+  unsigned long long *vflag_dev = nullptr;
+  uint64_t gens_next_id = 1;        // ids of zc_msm_generators handles created on this context
+  int gens_live = 0;
   void *basepoint_table = nullptr;  // fixed-base table (zc_fixed.cu), built on first use
   void *msm_graph_exec = nullptr;   // cudaGraphExec_t of the last MSM configuration
   zc_msm_key msm_key = {};
@@ -103,6 +114,10 @@ static inline int32_t zc_scratch(zc_ctx *ctx, int slot, size_t bytes, void **out
 
 // implemented in zc_peer.cu
 int32_t zc_peer_exchange_fold(zc_ctx *ctx, const uint64_t *partial, uint64_t *out);
+int32_t zc_peer_check_error(zc_ctx *ctx);
+// implemented in zc_kernels.cu (extern "C", not in the public header): enqueue a canonical-input check (kind 1 field, 2 scalar, 3 point) / read the verdict
+extern "C" int32_t zc_validate_dev(zc_ctx *ctx, int32_t kind, const uint64_t *a, size_t n, size_t base);
+extern "C" int32_t zc_validate_finish(zc_ctx *ctx, int32_t elems_per_unit);
 // implemented in zc_msm.cu
-int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits,
-                   int32_t rank, int32_t nranks, bool exchange, uint64_t *out_point_dev);
+int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *points, const uint64_t *scalars, size_t n,
+                   int32_t window_bits, int32_t rank, int32_t nranks, bool exchange, uint64_t *out_point_dev);

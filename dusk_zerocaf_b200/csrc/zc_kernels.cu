@@ -59,6 +59,34 @@ __global__ void __launch_bounds__(TPB) fe_mul_square_kernel(const uint64_t* __re
   fe_store52(sq + 5 * i, fe_sqr_normal_pre<M>(x));
 }
 
+// ---- K1 fused on the 32-byte wire format (FieldElement::to_bytes / from_bytes, field.rs:563-631): the little-endian
+// encoding of a canonical value IS its eight 32-bit words, so an element is two 16-byte loads and the kernel moves the
+// algorithmic 128 bytes per pair (the [u64;5] limb layout moves 160).  Same values, bit for bit.
+template <int S>
+__device__ __forceinline__ Fe fe_load32_shl(const uint8_t* __restrict__ p) {
+  const uint4 lo = *reinterpret_cast<const uint4*>(p), hi = *reinterpret_cast<const uint4*>(p + 16);
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  Fe r;
+  r.w[0] = w[0] << S;
+#pragma unroll
+  for (int k = 1; k < 8; k++) r.w[k] = __funnelshift_l(w[k - 1], w[k], S);
+  return r;
+}
+__device__ __forceinline__ void fe_store32(uint8_t* __restrict__ p, const Fe& a) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a.w[0], a.w[1], a.w[2], a.w[3]);
+  *reinterpret_cast<uint4*>(p + 16) = make_uint4(a.w[4], a.w[5], a.w[6], a.w[7]);
+}
+template <class M>
+__global__ void __launch_bounds__(TPB) fe_mul_square_packed_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                                   uint8_t* __restrict__ prod, uint8_t* __restrict__ sq, size_t n) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const Fe x = fe_load32_shl<Shape<M>::SA>(a + 32 * i);
+  const Fe y = fe_load32_shl<Shape<M>::SB>(b + 32 * i);
+  fe_store32(prod + 32 * i, fe_mul_normal_pre<M>(x, y));
+  fe_store32(sq + 32 * i, fe_sqr_normal_pre<M>(x));
+}
+
 // ---- K2: point add / sub / double / neg on the ABI layout, limb-exact (edwards.rs:440-592) ----------------
 enum PtOp { PT_ADD = 0, PT_SUB = 1, PT_DOUBLE = 2, PT_NEG = 3 };
 
@@ -306,9 +334,67 @@ __global__ void point_fold_kernel(const uint64_t* __restrict__ pts, size_t k, ui
 
 inline unsigned grid_for(size_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
+// ---- input validation (opt-in: zc_ctx_set_validation, zc_*_check_canonical_batch) ---------------------------------
+// The reference's types expose their limbs (`pub [u64;5]`), and its own tests build non-canonical values on purpose
+// (field.rs:1160-1167, 1193-1200: operands with FIELD_L added).  The kernels here assume canonical inputs (limbs < 2^52,
+// value < modulus): with validation on, every element of every input array is checked on the device and the first
+// offending element index (array order: a, then b) comes back as ZC_ERR_NONCANONICAL instead of a silently wrong result.
+template <class M>
+__global__ void __launch_bounds__(TPB) check_canonical_kernel(const uint64_t* __restrict__ a, size_t n, unsigned long long base,
+                                                              unsigned long long* __restrict__ first_bad) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* p = a + 5 * i;
+  const uint64_t l0 = p[0], l1 = p[1], l2 = p[2], l3 = p[3], l4 = p[4];
+  bool bad = ((l0 | l1 | l2 | l3) >> 52) != 0 || (l4 >> 48) != 0;      // 4 x 52 + 48 = 256 bits
+  if (!bad) {
+    Fe x = fe_from_limbs52(l0, l1, l2, l3, l4);
+    Fe y = x;
+    reduce_once<M>(y);                                                   // y != x  <=>  x >= m
+    bad = !fe_eq(x, y);
+  }
+  if (bad) atomicMin(first_bad, base + (unsigned long long)i);
+}
+
+int32_t validation_setup(zc_ctx* ctx) {
+  if (ctx->vflag_dev) return ZC_OK;
+  ZC_CUDA(ctx, cudaMalloc(&ctx->vflag_dev, 8));
+  ZC_CUDA(ctx, cudaMemsetAsync(ctx->vflag_dev, 0xff, 8, ctx->stream));
+  return ZC_OK;
+}
+// enqueue the check of n_elems residues (a point is four) on the context's stream
+template <class M>
+int32_t validation_enqueue(zc_ctx* ctx, const uint64_t* a, size_t n_elems, size_t base) {
+  int32_t rc;
+  if ((rc = validation_setup(ctx))) return rc;
+  if (n_elems == 0 || !a) return ZC_OK;
+  check_canonical_kernel<M><<<grid_for(n_elems, TPB), TPB, 0, ctx->stream>>>(a, n_elems, (unsigned long long)base, ctx->vflag_dev);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+// wait, read the verdict, re-arm.  elems_per_unit: 1 (field / scalar arrays) or 4 (points) for the index in the message
+int32_t validation_finish(zc_ctx* ctx, int elems_per_unit, unsigned long long* first_bad_out) {
+  if (!ctx->vflag_dev) return ZC_OK;
+  unsigned long long v = 0;
+  ZC_CUDA(ctx, cudaMemcpyAsync(&v, ctx->vflag_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ZC_CUDA(ctx, cudaMemsetAsync(ctx->vflag_dev, 0xff, 8, ctx->stream));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (v == ~0ull) return ZC_OK;
+  if (first_bad_out) *first_bad_out = v / (unsigned long long)elems_per_unit;
+  snprintf(ctx->err, sizeof(ctx->err), "non-canonical input (limb >= 2^52 or value >= modulus): first offending element %llu",
+           v / (unsigned long long)elems_per_unit);
+  return ZC_ERR_NONCANONICAL;
+}
+
 template <class M, int OP>
 int32_t launch_fe(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
   if (n == 0) return ZC_OK;
+  if (ctx->validate) {
+    int32_t rc;
+    if ((rc = validation_enqueue<M>(ctx, a, n, ctx->vbase))) return rc;
+    if (b && (rc = validation_enqueue<M>(ctx, b, n, ctx->vbase))) return rc;
+  }
   fe_op_kernel<M, OP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(a, b, out, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
@@ -317,6 +403,11 @@ int32_t launch_fe(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* o
 template <int OP>
 int32_t launch_pt(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
   if (n == 0) return ZC_OK;
+  if (ctx->validate) {
+    int32_t rc;
+    if ((rc = validation_enqueue<ModP>(ctx, p, 4 * n, 4 * ctx->vbase))) return rc;
+    if (q && (rc = validation_enqueue<ModP>(ctx, q, 4 * n, 4 * ctx->vbase))) return rc;
+  }
   pt_op_kernel<OP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(p, q, out, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
@@ -366,7 +457,12 @@ int32_t host_pipelined(zc_ctx* ctx, size_t n, HostArr* ins, int n_in, HostArr* o
                                    cnt * ins[i].stride, cudaMemcpyHostToDevice, ctx->copy_in));
     ZC_CUDA(ctx, cudaEventRecord(ev_in, ctx->copy_in));
     ZC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
-    if ((rc = launch(i0, cnt))) return rc;
+    ctx->vbase = i0;
+    ctx->in_pipeline = true;                      // _dev entry points called from a chunk do not read the verdict back (the caller does, once)
+    rc = launch(i0, cnt);
+    ctx->in_pipeline = false;
+    ctx->vbase = 0;
+    if (rc) return rc;
     ZC_CUDA(ctx, cudaEventRecord(ev_done, ctx->stream));
     ZC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_done, 0));
     for (int i = 0; i < n_out; i++)
@@ -432,11 +528,11 @@ int32_t zc_ctx_destroy(zc_ctx* ctx) {
   for (int i = 0; i < 6; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->msm_ws) cudaFree(ctx->msm_ws);
   if (ctx->basepoint_table) cudaFree(ctx->basepoint_table);
-  if (ctx->fb_table) cudaFree(ctx->fb_table);
-  if (ctx->fb_corr) cudaFree(ctx->fb_corr);
   if (ctx->gather_buf) cudaFree(ctx->gather_buf);
-  if (ctx->peers_connected) for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && ctx->peers.p[r]) cudaIpcCloseMemHandle(ctx->peers.p[r]);
+  if (ctx->peers_connected && ctx->peers_ipc) for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && ctx->peers.p[r]) cudaIpcCloseMemHandle(ctx->peers.p[r]);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
+  if (ctx->vflag_dev) cudaFree(ctx->vflag_dev);
+  if (ctx->peer_error_host) cudaFreeHost(ctx->peer_error_host);
   if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); for (int i = 0; i < 2 * ZC_PIPE_MAX_CHUNKS; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]); }
   if (ctx->msm_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); cudaStreamSynchronize(ctx->chain_stream); cudaStreamDestroy(ctx->chain_stream); for (int i = 0; i < 3; i++) { if (ctx->side_extra[i]) cudaStreamDestroy(ctx->side_extra[i]); if (ctx->side_hi[i]) cudaStreamDestroy(ctx->side_hi[i]); } if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream); }
@@ -449,7 +545,7 @@ int32_t zc_ctx_destroy(zc_ctx* ctx) {
 int32_t zc_ctx_sync(zc_ctx* ctx) {
   ZC_CHECK_CTX(ctx);
   ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZC_OK;
+  return zc_peer_check_error(ctx);                  // a timed-out sharded exchange surfaces here (ZC_ERR_STATE), once
 }
 
 const char* zc_last_error_string(zc_ctx* ctx) { return ctx ? ctx->err : "null context"; }
@@ -481,30 +577,34 @@ int32_t zc_host_unregister(void* p) {
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, a && b && out);                                                                             \
-    return launch_fe<MOD, OP>(ctx, a, b, out, n);                                                                 \
+    int32_t rc_ = launch_fe<MOD, OP>(ctx, a, b, out, n);                                                          \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 1, nullptr) : rc_;                            \
   }                                                                                                               \
   int32_t NAME(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {                      \
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, a && b && out);                                                                             \
-    return host_binary(ctx, n, a, 40, b, 40, out, 40, [&](const void* da, const void* db, void* dout, size_t m) { \
+    int32_t rc_ = host_binary(ctx, n, a, 40, b, 40, out, 40, [&](const void* da, const void* db, void* dout, size_t m) { \
       return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, m);               \
     });                                                                                                           \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 1, nullptr) : rc_;                            \
   }
 #define ZC_DEFINE_UN(NAME, MOD, OP)                                                                               \
   int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t n) {                                   \
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, a && out);                                                                                  \
-    return launch_fe<MOD, OP>(ctx, a, nullptr, out, n);                                                           \
+    int32_t rc_ = launch_fe<MOD, OP>(ctx, a, nullptr, out, n);                                                    \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 1, nullptr) : rc_;                            \
   }                                                                                                               \
   int32_t NAME(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t n) {                                         \
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, a && out);                                                                                  \
-    return host_binary(ctx, n, a, 40, nullptr, 0, out, 40, [&](const void* da, const void*, void* dout, size_t m) { \
+    int32_t rc_ = host_binary(ctx, n, a, 40, nullptr, 0, out, 40, [&](const void* da, const void*, void* dout, size_t m) { \
       return launch_fe<MOD, OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, m);                           \
     });                                                                                                           \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 1, nullptr) : rc_;                            \
   }
 
 ZC_DEFINE_BIN(zc_fe_mul_batch, ModP, OP_MUL)
@@ -522,10 +622,15 @@ int32_t zc_fe_mul_square_batch_dev(zc_ctx* ctx, const uint64_t* a, const uint64_
   ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
   if (n == 0) return ZC_OK;
   ZC_CHECK_PTR(ctx, a && b && prod && sq);
+  if (ctx->validate) {
+    int32_t rc;
+    if ((rc = validation_enqueue<ModP>(ctx, a, n, ctx->vbase))) return rc;
+    if ((rc = validation_enqueue<ModP>(ctx, b, n, ctx->vbase))) return rc;
+  }
   fe_mul_square_kernel<ModP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(a, b, prod, sq, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
-  return ZC_OK;
+  return (ctx->validate && !ctx->in_pipeline) ? validation_finish(ctx, 1, nullptr) : ZC_OK;
 }
 int32_t zc_fe_mul_square_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* prod, uint64_t* sq, size_t n) {
   ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
@@ -533,9 +638,32 @@ int32_t zc_fe_mul_square_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b
   ZC_CHECK_PTR(ctx, a && b && prod && sq);
   HostArr ins[2] = {{a, nullptr, 40, 0, nullptr}, {b, nullptr, 40, 1, nullptr}};
   HostArr outs[2] = {{nullptr, prod, 40, 2, nullptr}, {nullptr, sq, 40, 3, nullptr}};
-  return host_pipelined(ctx, n, ins, 2, outs, 2, [&](size_t i0, size_t cnt) {
+  int32_t rc_ = host_pipelined(ctx, n, ins, 2, outs, 2, [&](size_t i0, size_t cnt) {
     return zc_fe_mul_square_batch_dev(ctx, (const uint64_t*)ins[0].d + 5 * i0, (const uint64_t*)ins[1].d + 5 * i0,
                                       (uint64_t*)outs[0].d + 5 * i0, (uint64_t*)outs[1].d + 5 * i0, cnt);
+  });
+  return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 1, nullptr) : rc_;
+}
+
+int32_t zc_fe_mul_square_batch_packed_dev(zc_ctx* ctx, const uint8_t* a, const uint8_t* b, uint8_t* prod, uint8_t* sq, size_t n) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, a && b && prod && sq);
+  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)prod | (uintptr_t)sq) & 15) != 0) return zc_fail(ctx, ZC_ERR_SIZE, "packed arrays must be 16-byte aligned");
+  fe_mul_square_packed_kernel<ModP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(a, b, prod, sq, n);
+  ctx->launches++;
+  ZC_CUDA(ctx, cudaGetLastError());
+  return ZC_OK;
+}
+int32_t zc_fe_mul_square_batch_packed(zc_ctx* ctx, const uint8_t* a, const uint8_t* b, uint8_t* prod, uint8_t* sq, size_t n) {
+  ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
+  if (n == 0) return ZC_OK;
+  ZC_CHECK_PTR(ctx, a && b && prod && sq);
+  HostArr ins[2] = {{a, nullptr, 32, 0, nullptr}, {b, nullptr, 32, 1, nullptr}};
+  HostArr outs[2] = {{nullptr, prod, 32, 2, nullptr}, {nullptr, sq, 32, 3, nullptr}};
+  return host_pipelined(ctx, n, ins, 2, outs, 2, [&](size_t i0, size_t cnt) {
+    return zc_fe_mul_square_batch_packed_dev(ctx, (const uint8_t*)ins[0].d + 32 * i0, (const uint8_t*)ins[1].d + 32 * i0,
+                                             (uint8_t*)outs[0].d + 32 * i0, (uint8_t*)outs[1].d + 32 * i0, cnt);
   });
 }
 
@@ -545,30 +673,34 @@ int32_t zc_fe_mul_square_batch(zc_ctx* ctx, const uint64_t* a, const uint64_t* b
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, p && q && out);                                                                             \
-    return launch_pt<OP>(ctx, p, q, out, n);                                                                      \
+    int32_t rc_ = launch_pt<OP>(ctx, p, q, out, n);                                                               \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 4, nullptr) : rc_;                            \
   }                                                                                                               \
   int32_t NAME(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {                      \
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, p && q && out);                                                                             \
-    return host_binary(ctx, n, p, 160, q, 160, out, 160, [&](const void* da, const void* db, void* dout, size_t m) { \
+    int32_t rc_ = host_binary(ctx, n, p, 160, q, 160, out, 160, [&](const void* da, const void* db, void* dout, size_t m) { \
       return launch_pt<OP>(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, m);                    \
     });                                                                                                           \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 4, nullptr) : rc_;                            \
   }
 #define ZC_DEFINE_PT_UN(NAME, OP)                                                                                 \
   int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* p, uint64_t* out, size_t n) {                                   \
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, p && out);                                                                                  \
-    return launch_pt<OP>(ctx, p, nullptr, out, n);                                                                \
+    int32_t rc_ = launch_pt<OP>(ctx, p, nullptr, out, n);                                                         \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 4, nullptr) : rc_;                            \
   }                                                                                                               \
   int32_t NAME(zc_ctx* ctx, const uint64_t* p, uint64_t* out, size_t n) {                                         \
     ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
     if (n == 0) return ZC_OK;                                                                                     \
     ZC_CHECK_PTR(ctx, p && out);                                                                                  \
-    return host_binary(ctx, n, p, 160, nullptr, 0, out, 160, [&](const void* da, const void*, void* dout, size_t m) { \
+    int32_t rc_ = host_binary(ctx, n, p, 160, nullptr, 0, out, 160, [&](const void* da, const void*, void* dout, size_t m) { \
       return launch_pt<OP>(ctx, (const uint64_t*)da, nullptr, (uint64_t*)dout, m);                                \
     });                                                                                                           \
+    return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 4, nullptr) : rc_;                            \
   }
 
 ZC_DEFINE_PT_BIN(zc_point_add_batch, PT_ADD)
@@ -599,6 +731,11 @@ int32_t zc_point_scalar_mul_batch_dev(zc_ctx* ctx, const uint64_t* points, const
   if (mode != ZC_SCALAR_MUL_STRICT && mode != ZC_SCALAR_MUL_FAST) return zc_fail(ctx, ZC_ERR_MODE, "unknown scalar-mul mode");
   if (n == 0) return ZC_OK;
   ZC_CHECK_PTR(ctx, points && scalars && out);
+  if (ctx->validate) {
+    int32_t rc;
+    if ((rc = validation_enqueue<ModP>(ctx, points, 4 * n, 4 * ctx->vbase))) return rc;
+    if ((rc = validation_enqueue<ModL>(ctx, scalars, n, ctx->vbase))) return rc;
+  }
   if (mode == ZC_SCALAR_MUL_STRICT) {
     scalar_mul_strict_kernel<<<grid_for(n, STRICT_TPB), STRICT_TPB, STRICT_RING * 8 * STRICT_TPB * 16, ctx->stream>>>(points, scalars, out, n);
   } else {
@@ -614,16 +751,17 @@ int32_t zc_point_scalar_mul_batch_dev(zc_ctx* ctx, const uint64_t* points, const
   }
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
-  return ZC_OK;
+  return (ctx->validate && !ctx->in_pipeline) ? validation_finish(ctx, 1, nullptr) : ZC_OK;
 }
 int32_t zc_point_scalar_mul_batch(zc_ctx* ctx, const uint64_t* points, const uint64_t* scalars, uint64_t* out, size_t n, int32_t mode) {
   ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);
   if (mode != ZC_SCALAR_MUL_STRICT && mode != ZC_SCALAR_MUL_FAST) return zc_fail(ctx, ZC_ERR_MODE, "unknown scalar-mul mode");
   if (n == 0) return ZC_OK;
   ZC_CHECK_PTR(ctx, points && scalars && out);
-  return host_binary(ctx, n, points, 160, scalars, 40, out, 160, [&](const void* da, const void* db, void* dout, size_t m) {
+  int32_t rc_ = host_binary(ctx, n, points, 160, scalars, 40, out, 160, [&](const void* da, const void* db, void* dout, size_t m) {
     return zc_point_scalar_mul_batch_dev(ctx, (const uint64_t*)da, (const uint64_t*)db, (uint64_t*)dout, m, mode);
   });
+  return (rc_ == ZC_OK && ctx->validate) ? validation_finish(ctx, 1, nullptr) : rc_;
 }
 
 int32_t zc_point_fold_dev(zc_ctx* ctx, const uint64_t* points_dev, size_t k, uint64_t* out_point_dev) {
@@ -634,5 +772,45 @@ int32_t zc_point_fold_dev(zc_ctx* ctx, const uint64_t* points_dev, size_t k, uin
   ZC_CUDA(ctx, cudaGetLastError());
   return ZC_OK;
 }
+
+
+// ---- validation API ---------------------------------------------------------------------------------------------
+int32_t zc_ctx_set_validation(zc_ctx* ctx, int32_t on) {
+  ZC_CHECK_CTX(ctx);
+  if (on) { int32_t rc = validation_setup(ctx); if (rc) return rc; }
+  ctx->validate = on != 0;
+  return ZC_OK;
+}
+int32_t zc_validate_dev(zc_ctx* ctx, int32_t kind, const uint64_t* a, size_t n, size_t base) {   // internal (zc_msm.cu): 1 field, 2 scalar, 3 point
+  if (kind == 2) return validation_enqueue<ModL>(ctx, a, n, base);
+  return validation_enqueue<ModP>(ctx, a, kind == 3 ? 4 * n : n, kind == 3 ? 4 * base : base);
+}
+int32_t zc_validate_finish(zc_ctx* ctx, int32_t elems_per_unit) { return validation_finish(ctx, elems_per_unit, nullptr); }
+
+#define ZC_DEFINE_CHECK(NAME, MOD, STRIDE_LIMBS)                                                                     \
+  int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* a, size_t n, uint64_t* first_bad) {                               \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, a);                                                                                         \
+    int32_t rc_ = validation_enqueue<MOD>(ctx, a, n * (STRIDE_LIMBS / 5), 0);                                     \
+    if (rc_) return rc_;                                                                                          \
+    unsigned long long fb = 0;                                                                                    \
+    rc_ = validation_finish(ctx, STRIDE_LIMBS / 5, &fb);                                                          \
+    if (rc_ == ZC_ERR_NONCANONICAL && first_bad) *first_bad = fb;                                                 \
+    return rc_;                                                                                                   \
+  }                                                                                                               \
+  int32_t NAME(zc_ctx* ctx, const uint64_t* a, size_t n, uint64_t* first_bad) {                                   \
+    ZC_CHECK_CTX(ctx); ZC_CHECK_N(ctx, n);                                                                        \
+    if (n == 0) return ZC_OK;                                                                                     \
+    ZC_CHECK_PTR(ctx, a);                                                                                         \
+    void* d = nullptr;                                                                                            \
+    int32_t rc_ = zc_scratch(ctx, 0, n * STRIDE_LIMBS * 8, &d);                                                   \
+    if (rc_) return rc_;                                                                                          \
+    ZC_CUDA(ctx, cudaMemcpyAsync(d, a, n * STRIDE_LIMBS * 8, cudaMemcpyHostToDevice, ctx->stream));               \
+    return NAME##_dev(ctx, (const uint64_t*)d, n, first_bad);                                                     \
+  }
+ZC_DEFINE_CHECK(zc_fe_check_canonical_batch, ModP, 5)
+ZC_DEFINE_CHECK(zc_scalar_check_canonical_batch, ModL, 5)
+ZC_DEFINE_CHECK(zc_point_check_canonical_batch, ModP, 20)
 
 }  // extern "C"

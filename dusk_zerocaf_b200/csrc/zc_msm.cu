@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(32) msm_chain_kernel(const uint32_t* __restric
   const int lane = threadIdx.x;
   const int q = lane & 3, qbase = lane & ~3;
   Pt a0 = first ? pt_identity_mont() : ld_pt(acc_io);
-  Fe c = (q == 0) ? a0.X : (q == 1 ? a0.Y : (q == 2 ? a0.Z : a0.T));
+  Fe c = pt_coord(a0, q);
 #pragma unroll 1
   for (int i = 0; i < ng; i++) {
     const uint32_t* cw = comp - 128 * (ptrdiff_t)i;          // windows in descending order
@@ -838,8 +838,20 @@ __global__ void msm_stamp_kernel(unsigned long long* slot) {
 // ---------------------------------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t c,
+int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t c,
                    int32_t rank, int32_t nranks, bool exchange, uint64_t *out_point_dev) {
+  if (ctx->validate && n) {                                       // scalars >= L (or limbs >= 2^52) would land in wrong buckets silently
+    int32_t rc;
+    if (points && !gens && (rc = zc_validate_dev(ctx, 3, points, n, 0))) return rc;
+    if (scalars && (rc = zc_validate_dev(ctx, 2, scalars, gens ? gens->n : n, 0))) return rc;
+    if ((rc = zc_validate_finish(ctx, 1))) return rc;
+  }
+  if (gens) {
+    if (gens->owner != ctx) return zc_fail(ctx, ZC_ERR_STATE, "generator handle belongs to another context");
+    if (gens->kind == ZC_GEN_FIXED_BASE && (gens->c != c || gens->rank != rank || gens->nranks != nranks))
+      return zc_fail(ctx, ZC_ERR_MODE, "fixed-base tables were built for another (window_bits, rank, nranks)");
+    n = gens->n;
+  }
   if (c < 8 || c > 16) return zc_fail(ctx, ZC_ERR_MODE, "window_bits must be in 8..16");
   if (nranks < 1 || rank < 0 || rank >= nranks) return zc_fail(ctx, ZC_ERR_SIZE, "bad rank / nranks");
   if (n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "n exceeds 2^31 - 1");
@@ -859,6 +871,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
   wmap.merged = 0;
 
   uint64_t *partial = exchange ? nullptr : out_point_dev;
+  if (exchange) ctx->peer_seq++;                                  // counted before anything can fail: the ranks' sequence numbers never drift apart
   if (exchange) {
     if (!ctx->nccl_comm && !ctx->peers_connected) return zc_fail(ctx, ZC_ERR_STATE, "zc_msm_sharded_dev needs zc_peer_mailbox_connect or zc_ctx_set_nccl first");
     partial = (uint64_t*)ctx->gather_buf + 20 * (size_t)nranks;   // send slot after the nranks receive slots
@@ -871,15 +884,14 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
   } else {
     // fixed-base tables prepared for exactly this call shape (zc_msm_prepare_fixed_base_dev): every (window, point) entry is
     // a row of the table, all of the rank's windows share one bucket set, and there is no doubling chain
-    const bool use_fb = points && ctx->fb_table && ctx->fb_points == (const void*)points && ctx->fb_n == n && ctx->fb_c == c &&
-                        ctx->fb_rank == rank && ctx->fb_nranks == nranks;
+    const bool use_fb = gens && gens->kind == ZC_GEN_FIXED_BASE;
     const int nwb = use_fb ? 1 : nwl;                           // bucket sets
     wmap.merged = use_fb ? 1 : 0;
     const size_t fb_entries = (size_t)nwl * n;
     const int fb_seg = fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8);
     // workspace layout
     size_t o = 0;
-    size_t o_cached = o; o = align_up(o + (use_fb ? 0 : n * 128), 256);
+    size_t o_cached = o; o = align_up(o + (gens ? 0 : n * 128), 256);
     size_t o_digits = o; o = align_up(o + (size_t)nwl * n * 4, 256);
     // Segment length, per task group: 32 when the group holds >= 2^22 entries, 16 below that, 8 for <= 2^19 -- less work
     // gets shorter segments so that the accumulation still fills the GPU (one window of 2^20 points in 32-entry segments
@@ -912,12 +924,12 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     size_t o_comp = o; o = align_up(o + (size_t)nwb * 4 * 128, 256);
     if (o > ctx->msm_ws_bytes) {
       if (ctx->msm_ws) ZC_CUDA(ctx, cudaFree(ctx->msm_ws));
-      ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0; ctx->prep_valid = false;
+      ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0;
       ZC_CUDA(ctx, cudaMalloc(&ctx->msm_ws, o));
       ctx->msm_ws_bytes = o;
     }
     char *ws = (char*)ctx->msm_ws;
-    uint32_t *cached = (uint32_t*)(ws + o_cached);
+    uint32_t *cached = gens ? (uint32_t*)gens->cached : (uint32_t*)(ws + o_cached);
     int32_t *digits = (int32_t*)(ws + o_digits);
     uint32_t *sorted = (uint32_t*)(ws + o_sorted);
     uint32_t *hist = (uint32_t*)(ws + o_hist);
@@ -967,13 +979,8 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
     // The ~25 launches and the two-stream fork/join of one MSM are recorded once into a CUDA graph and replayed while
     // the call's arguments stay the same (repeated proofs over resident generators): one launch instead of a launch-
     // latency-bound sequence -- at 8 ranks the per-rank kernels are short enough for launch gaps to rival the math.
-    // prepared points (zc_msm_prepare_points_dev): the cached operands at the head of the workspace are reused
-    const bool use_prepared = !use_fb && points && ctx->prep_points == (const void*)points && ctx->prep_n == n;
-    if (!use_prepared) ctx->prep_valid = false;                // this call's operand pass overwrites the cached array
-    if (use_prepared && !ctx->prep_valid) {                    // the workspace was reallocated / reused since: prepare again
-      msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(points, cached, n); ctx->launches++;
-      ctx->prep_valid = true;
-    }
+    // generator handle (zc_msm_generators_create_dev): the operand pass ran once, the handle owns the cached array
+    const bool use_prepared = gens && gens->kind == ZC_GEN_PREPARED;
     uint64_t nlaunch = 0;
     // ZC_MSM_TRACE=1: no graph, a timing event after every kernel, timeline printed to stderr (development aid).
     // ZC_MSM_TRACE=2: the graph as usual, with a one-thread %globaltimer stamp after every kernel; timeline printed
@@ -1052,7 +1059,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         // inline by the reduction's loads, the few heavier ones (buckets the short top window also feeds) one warp each.
         const int seg = fb_seg, nseg = (int)(n_pad / seg);
         const int fix_inline = 2 * (int)(fb_entries / ((size_t)nb * seg)) + FIX_INLINE;
-        msm_accum_kernel<true><<<(unsigned)((nseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>((const uint32_t*)ctx->fb_table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
+        msm_accum_kernel<true><<<(unsigned)((nseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
         nlaunch++; mark(st, 0, "msm_accum_kernel");
         msm_fixq_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(offs, hist, seg, 1, nb, fix_inline, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_fixq_kernel");
         msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_heavy_kernel");
@@ -1064,7 +1071,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
         msm_cube2b_kernel<<<4, 128, 0, st>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(st, 0, "msm_cube2b_kernel");
         ChainGaps gaps;
         for (int i = 0; i < MAX_WINDOWS; i++) gaps.pre[i] = 0;
-        msm_chain_kernel<<<1, 32, 0, st>>>(comp, 1, 1, a1, a2, 0, gaps, 0, acc, partial, (const uint64_t*)ctx->fb_corr); nlaunch++; mark(st, 0, "msm_chain_kernel");
+        msm_chain_kernel<<<1, 32, 0, st>>>(comp, 1, 1, a1, a2, 0, gaps, 0, acc, partial, (const uint64_t*)gens->corr); nlaunch++; mark(st, 0, "msm_chain_kernel");
         ZC_CUDA(ctx, cudaGetLastError());
         return ZC_OK;
       }
@@ -1161,7 +1168,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
       ZC_CUDA(ctx, cudaGetLastError());
       return ZC_OK;
     };
-    const zc_msm_key key = {points, scalars, n, c, rank, nranks, use_fb ? 2 : (use_prepared ? 1 : 0), partial, ctx->msm_ws};
+    zc_msm_key key;
+    memset(&key, 0, sizeof(key));                               // padding bytes take part in the memcmp below
+    key.points = gens ? nullptr : points; key.scalars = scalars; key.n = n; key.c = c; key.rank = rank; key.nranks = nranks;
+    key.mode = use_fb ? 2 : (use_prepared ? 1 : 0); key.partial = partial; key.ws = ctx->msm_ws; key.gens_id = gens ? gens->id : 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     ZC_CUDA(ctx, cudaStreamIsCapturing(st, &cap));
     if (cap != cudaStreamCaptureStatusNone || trace) {
@@ -1223,92 +1233,118 @@ int32_t zc_msm_run(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
 
 extern "C" {
 
-int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points, size_t n) {
+// ---- fixed generators: an opaque handle that owns everything derived from the points ---------------------------------
+int32_t zc_msm_generators_create_dev(zc_ctx *ctx, const uint64_t *points, size_t n, int32_t kind, int32_t window_bits,
+                                     int32_t rank, int32_t nranks, zc_msm_generators **out) {
   if (!ctx) return ZC_ERR_NULL;
   ZC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!out) return zc_fail(ctx, ZC_ERR_NULL, "null handle pointer");
+  *out = nullptr;
   if (!points || n == 0) return zc_fail(ctx, ZC_ERR_NULL, "null / empty points");
   if (n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "n exceeds 2^31 - 1");
-  const size_t need = align_up(n * 128, 256);
-  if (need > ctx->msm_ws_bytes) {
-    if (ctx->msm_ws) ZC_CUDA(ctx, cudaFree(ctx->msm_ws));
-    ctx->msm_ws = nullptr; ctx->msm_ws_bytes = 0;
-    ZC_CUDA(ctx, cudaMalloc(&ctx->msm_ws, need));
-    ctx->msm_ws_bytes = need;
-  }
-  msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)ctx->msm_ws, n);
-  ctx->launches++;
-  ZC_CUDA(ctx, cudaGetLastError());
-  ctx->prep_points = points; ctx->prep_n = n; ctx->prep_valid = true;
-  return ZC_OK;
-}
-
-int32_t zc_msm_prepare_fixed_base_dev(zc_ctx *ctx, const uint64_t *points, size_t n, int32_t window_bits, int32_t rank, int32_t nranks) {
-  if (!ctx) return ZC_ERR_NULL;
-  ZC_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!points || n == 0) return zc_fail(ctx, ZC_ERR_NULL, "null / empty points");
+  if (kind != ZC_GEN_PREPARED && kind != ZC_GEN_FIXED_BASE) return zc_fail(ctx, ZC_ERR_MODE, "kind must be ZC_GEN_PREPARED or ZC_GEN_FIXED_BASE");
   const int c = window_bits;
-  if (c < 8 || c > 16) return zc_fail(ctx, ZC_ERR_MODE, "window_bits must be in 8..16");
-  if (nranks < 1 || rank < 0 || rank >= nranks) return zc_fail(ctx, ZC_ERR_SIZE, "bad rank / nranks");
   FbWindows win;
   win.nwl = 0;
-  const int nwin = (256 + c - 1) / c;
-  for (int w = 0; w < nwin; w++) if (w % nranks == rank) win.w[win.nwl++] = (int16_t)w;
-  for (int t = win.nwl; t < MAX_WINDOWS; t++) win.w[t] = 0;
-  if ((size_t)win.nwl * n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "windows x points exceeds 2^31 - 1");
-  // a recorded graph may hold the old table's address
-  if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
-  ctx->fb_points = nullptr;
-  const size_t need = (size_t)win.nwl * n * 128;
-  if (need > ctx->fb_table_bytes) {
-    if (ctx->fb_table) ZC_CUDA(ctx, cudaFree(ctx->fb_table));
-    ctx->fb_table = nullptr; ctx->fb_table_bytes = 0;
-    ZC_CUDA(ctx, cudaMalloc(&ctx->fb_table, need));
-    ctx->fb_table_bytes = need;
+  if (kind == ZC_GEN_FIXED_BASE) {
+    if (c < 8 || c > 16) return zc_fail(ctx, ZC_ERR_MODE, "window_bits must be in 8..16");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return zc_fail(ctx, ZC_ERR_SIZE, "bad rank / nranks");
+    const int nwin = (256 + c - 1) / c;
+    for (int w = 0; w < nwin; w++) if (w % nranks == rank) win.w[win.nwl++] = (int16_t)w;
+    for (int t = win.nwl; t < MAX_WINDOWS; t++) win.w[t] = 0;
+    if ((size_t)win.nwl * n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "windows x points exceeds 2^31 - 1");
   }
-  if (win.nwl > 0) {
-    msm_fixed_base_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)ctx->fb_table, n, c, win);
+  zc_msm_generators *g = new zc_msm_generators();
+  g->id = ctx->gens_next_id++; g->owner = ctx; g->kind = kind; g->n = n;
+  g->c = kind == ZC_GEN_FIXED_BASE ? c : 0; g->rank = kind == ZC_GEN_FIXED_BASE ? rank : 0; g->nranks = kind == ZC_GEN_FIXED_BASE ? nranks : 0;
+  g->cached = nullptr; g->table = nullptr; g->table_bytes = 0; g->corr = nullptr;
+  auto fail = [&](int32_t rc) { cudaFree(g->cached); cudaFree(g->table); cudaFree(g->corr); delete g; return rc; };
+#define ZC_GEN_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(-(int32_t)e__); } } while (0)
+  if (kind == ZC_GEN_PREPARED) {
+    // normalise to Z = 1 once (one inversion per point): every later bucket addition is a 7-multiplication mixed addition
+    ZC_GEN_CUDA(cudaMalloc(&g->cached, n * 128));
+    msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)g->cached, n);
     ctx->launches++;
-    ZC_CUDA(ctx, cudaGetLastError());
+    ZC_GEN_CUDA(cudaGetLastError());
+  } else {
+    g->table_bytes = (size_t)win.nwl * n * 128;
+    if (win.nwl > 0) {
+      ZC_GEN_CUDA(cudaMalloc(&g->table, g->table_bytes));
+      msm_fixed_base_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)g->table, n, c, win);
+      ctx->launches++;
+      ZC_GEN_CUDA(cudaGetLastError());
+    }
+    // spread short window (at most one per scalar width): the constant it adds to every MSM, negated, kept for the chain kernel
+    for (int t = 0; t < win.nwl; t++) {
+      const int sm = merged_spread_bits(c, win.w[t]);
+      if (sm == 0) continue;
+      void *ks = nullptr;
+      int32_t rc;
+      if ((rc = zc_scratch(ctx, 1, n * 40 + 8, &ks))) return fail(rc);
+      ZC_GEN_CUDA(cudaMalloc(&g->corr, 160));
+      msm_spread_scalars_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint64_t*)ks, n, sm, c * win.w[t] - sm);
+      ctx->launches++;
+      if ((rc = zc_msm_run(ctx, nullptr, points, (const uint64_t*)ks, n, c, 0, 1, false, (uint64_t*)g->corr))) return fail(rc);
+      if ((rc = zc_point_neg_batch_dev(ctx, (const uint64_t*)g->corr, (uint64_t*)g->corr, 1))) return fail(rc);
+    }
   }
-  // spread short window (at most one per scalar width): the constant it adds to every MSM, negated, kept for the chain kernel
-  if (ctx->fb_corr) { ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ZC_CUDA(ctx, cudaFree(ctx->fb_corr)); ctx->fb_corr = nullptr; }
-  for (int t = 0; t < win.nwl; t++) {
-    const int sm = merged_spread_bits(c, win.w[t]);
-    if (sm == 0) continue;
-    void *ks = nullptr;
-    int32_t rc;
-    if ((rc = zc_scratch(ctx, 1, n * 40 + 8, &ks))) return rc;
-    ZC_CUDA(ctx, cudaMalloc(&ctx->fb_corr, 160));
-    msm_spread_scalars_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint64_t*)ks, n, sm, c * win.w[t] - sm);
-    ctx->launches++;
-    if ((rc = zc_msm_run(ctx, points, (const uint64_t*)ks, n, c, 0, 1, false, (uint64_t*)ctx->fb_corr))) return rc;
-    if ((rc = zc_point_neg_batch_dev(ctx, (const uint64_t*)ctx->fb_corr, (uint64_t*)ctx->fb_corr, 1))) return rc;
-    if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
-  }
-  ctx->fb_points = points; ctx->fb_n = n; ctx->fb_c = c; ctx->fb_rank = rank; ctx->fb_nranks = nranks;
+  // the caller's point array is not referenced after this returns
+  ZC_GEN_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef ZC_GEN_CUDA
+  ctx->gens_live++;
+  *out = g;
   return ZC_OK;
 }
 
-int32_t zc_msm_forget_points(zc_ctx *ctx) {
+int32_t zc_msm_generators_destroy(zc_ctx *ctx, zc_msm_generators *gens) {
+  if (!ctx) return ZC_ERR_NULL;
+  if (!gens) return ZC_OK;
+  if (gens->owner != ctx) return zc_fail(ctx, ZC_ERR_STATE, "generator handle belongs to another context");
+  ZC_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // an enqueued MSM may still read the tables
+  if (ctx->msm_graph_exec && ctx->msm_key.gens_id == gens->id) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
+  cudaFree(gens->cached); cudaFree(gens->table); cudaFree(gens->corr);
+  gens->owner = nullptr;
+  delete gens;
+  ctx->gens_live--;
+  return ZC_OK;
+}
+
+int32_t zc_msm_generators_info(const zc_msm_generators *gens, size_t *n, int32_t *kind, size_t *device_bytes) {
+  if (!gens) return ZC_ERR_NULL;
+  if (n) *n = gens->n;
+  if (kind) *kind = gens->kind;
+  if (device_bytes) *device_bytes = (gens->cached ? gens->n * 128 : 0) + gens->table_bytes + (gens->corr ? 160 : 0);
+  return ZC_OK;
+}
+
+int32_t zc_msm_gen_dev(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *scalars, int32_t window_bits, uint64_t *out_point_dev) {
   if (!ctx) return ZC_ERR_NULL;
   ZC_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->prep_points = nullptr; ctx->prep_n = 0; ctx->prep_valid = false;
-  if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
-  if (ctx->fb_table) {
-    ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ZC_CUDA(ctx, cudaFree(ctx->fb_table));
-  }
-  if (ctx->fb_corr) ZC_CUDA(ctx, cudaFree(ctx->fb_corr));
-  ctx->fb_table = nullptr; ctx->fb_table_bytes = 0; ctx->fb_corr = nullptr;
-  ctx->fb_points = nullptr; ctx->fb_n = 0; ctx->fb_c = 0;
-  return ZC_OK;
+  if (!gens || !scalars || !out_point_dev) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");
+  return zc_msm_run(ctx, gens, nullptr, scalars, gens->n, window_bits, 0, 1, false, out_point_dev);
+}
+
+int32_t zc_msm_gen_partial_dev(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *scalars, int32_t window_bits,
+                               int32_t rank, int32_t nranks, uint64_t *out_point_dev) {
+  if (!ctx) return ZC_ERR_NULL;
+  ZC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!gens || !scalars || !out_point_dev) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");
+  return zc_msm_run(ctx, gens, nullptr, scalars, gens->n, window_bits, rank, nranks, false, out_point_dev);
+}
+
+int32_t zc_msm_gen_sharded_dev(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *scalars, int32_t window_bits, uint64_t *out_point_dev) {
+  if (!ctx) return ZC_ERR_NULL;
+  ZC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!gens || !scalars || !out_point_dev) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");
+  return zc_msm_run(ctx, gens, nullptr, scalars, gens->n, window_bits, ctx->rank, ctx->nranks, true, out_point_dev);
 }
 
 int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev) {
   if (!ctx) return ZC_ERR_NULL;
   ZC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!out_point_dev || (n && (!points || !scalars))) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");
-  return zc_msm_run(ctx, points, scalars, n, window_bits, 0, 1, false, out_point_dev);
+  return zc_msm_run(ctx, nullptr, points, scalars, n, window_bits, 0, 1, false, out_point_dev);
 }
 
 int32_t zc_msm_partial_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits,
@@ -1316,17 +1352,19 @@ int32_t zc_msm_partial_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *
   if (!ctx) return ZC_ERR_NULL;
   ZC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!out_point_dev || (n && (!points || !scalars))) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");
-  return zc_msm_run(ctx, points, scalars, n, window_bits, rank, nranks, false, out_point_dev);
+  return zc_msm_run(ctx, nullptr, points, scalars, n, window_bits, rank, nranks, false, out_point_dev);
 }
 
 int32_t zc_msm_sharded_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev) {
   if (!ctx) return ZC_ERR_NULL;
   ZC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!out_point_dev || (n && (!points || !scalars))) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");
-  return zc_msm_run(ctx, points, scalars, n, window_bits, ctx->rank, ctx->nranks, true, out_point_dev);
+  return zc_msm_run(ctx, nullptr, points, scalars, n, window_bits, ctx->rank, ctx->nranks, true, out_point_dev);
 }
 
-int32_t zc_msm(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point) {
+// host-pointer MSM: the scalars travel first so that digit extraction and the sort run under the (4x larger) copy of the
+// points; then one run on the resident arrays.  sharded != 0: every rank passes the same arrays (collective).
+static int32_t msm_host(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, bool sharded, uint64_t *out_point) {
   if (!ctx) return ZC_ERR_NULL;
   ZC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!out_point || (n && (!points || !scalars))) return zc_fail(ctx, ZC_ERR_NULL, "null pointer argument");
@@ -1336,13 +1374,21 @@ int32_t zc_msm(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, siz
   if ((rc = zc_scratch(ctx, 1, n * 40 + 8, &ds))) return rc;
   if ((rc = zc_scratch(ctx, 2, 160, &dout))) return rc;
   if (n) {
-    ZC_CUDA(ctx, cudaMemcpyAsync(dp, points, n * 160, cudaMemcpyHostToDevice, ctx->stream));
     ZC_CUDA(ctx, cudaMemcpyAsync(ds, scalars, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+    ZC_CUDA(ctx, cudaMemcpyAsync(dp, points, n * 160, cudaMemcpyHostToDevice, ctx->stream));
   }
-  if ((rc = zc_msm_run(ctx, (const uint64_t*)dp, (const uint64_t*)ds, n, window_bits, 0, 1, false, (uint64_t*)dout))) return rc;
+  if ((rc = zc_msm_run(ctx, nullptr, (const uint64_t*)dp, (const uint64_t*)ds, n, window_bits, sharded ? ctx->rank : 0, sharded ? ctx->nranks : 1,
+                       sharded, (uint64_t*)dout))) return rc;
   ZC_CUDA(ctx, cudaMemcpyAsync(out_point, dout, 160, cudaMemcpyDeviceToHost, ctx->stream));
   ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZC_OK;
+  return sharded ? zc_peer_check_error(ctx) : ZC_OK;
+}
+
+int32_t zc_msm(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point) {
+  return msm_host(ctx, points, scalars, n, window_bits, false, out_point);
+}
+int32_t zc_msm_sharded(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point) {
+  return msm_host(ctx, points, scalars, n, window_bits, true, out_point);
 }
 
 }  // extern "C"

@@ -117,6 +117,14 @@ __device__ __forceinline__ void quad_pick(Fe& u, Fe& v, const Fe& E, const Fe& F
     v.w[k] = selp_u32(F.w[k], selp_u32(G.w[k], H.w[k], q2), q0);       // F H G H
   }
 }
+// coordinate q of a point every lane holds in full
+__device__ __forceinline__ Fe pt_coord(const Pt& p, int q) {
+  Fe r;
+  const int q0 = q == 0, q1 = q == 1, q2 = q == 2;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.w[k] = selp_u32(p.X.w[k], selp_u32(p.Y.w[k], selp_u32(p.Z.w[k], p.T.w[k], q2), q1), q0);
+  return r;
+}
 // x * k mod p for x < 2^256, k < 2^18: result < 2m
 __device__ __forceinline__ Fe fe_mul_small(const Fe& x, uint32_t k) {
   typedef ModP M;
@@ -227,8 +235,8 @@ __device__ __forceinline__ Fe quad_add_inl(const Fe& c, const Pt& p, int q, int 
 }
 
 // out-of-line copies for kernels with several call sites (one body in the instruction cache)
-__device__ __noinline__ Fe quad_double(Fe c, int q, int qbase) { return quad_double_inl(c, q, qbase); }
-__device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) { return quad_add_inl(c, p, q, qbase); }
+static __device__ __noinline__ Fe quad_double(Fe c, int q, int qbase) { return quad_double_inl(c, q, qbase); }
+static __device__ __noinline__ Fe quad_add(Fe c, Pt p, int q, int qbase) { return quad_add_inl(c, p, q, qbase); }
 
 // x < 4m -> canonical
 __device__ __forceinline__ Fe fe_canon4(Fe x) {

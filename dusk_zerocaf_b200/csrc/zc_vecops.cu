@@ -136,6 +136,24 @@ __global__ void __launch_bounds__(TPB) window_naf_kernel(const uint64_t* __restr
   }
 }
 
+// Scalar::into_bits (scalar.rs:352-366): the 256 bits of the value, least significant first, one byte each.
+// One thread per (scalar, 16-bit group): 16-byte stores, coalesced.
+__global__ void __launch_bounds__(TPB) into_bits_kernel(const uint64_t* __restrict__ a, uint8_t* __restrict__ out, size_t n) {
+  size_t g = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (g >= 16 * n) return;
+  const size_t i = g >> 4;
+  const int grp = (int)(g & 15);
+  const Fe x = fe_load52(a + 5 * i);
+  const uint32_t bits = (x.w[grp >> 1] >> (16 * (grp & 1))) & 0xffffu;
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t nib = (bits >> (4 * k)) & 15u;
+    o[k] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+  }
+  *reinterpret_cast<uint4*>(out + 256 * i + 16 * grp) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // small synchronous host wrappers
 template <class F>
 int32_t host_run(zc_ctx* ctx, const void* in0, size_t in0_bytes, const void* in1, size_t in1_bytes, void* out, size_t out_bytes,
@@ -251,6 +269,20 @@ int32_t zc_scalar_window_naf_batch(zc_ctx* ctx, const uint64_t* a, int32_t width
   if (width < 2 || width > 7) return zc_fail(ctx, ZC_ERR_MODE, "NAF width must be in 2..7 (digits are i8)");
   return host_run(ctx, a, n * 40, nullptr, 0, out_digits, n * 256, nullptr, 0, [&](void* d0, void*, void* dout, void*) {
     return zc_scalar_window_naf_batch_dev(ctx, (const uint64_t*)d0, width, (int8_t*)dout, n);
+  });
+}
+
+
+int32_t zc_scalar_into_bits_batch_dev(zc_ctx* ctx, const uint64_t* a, uint8_t* out_bits, size_t n) {
+  ZC_VEC_PROLOGUE(ctx, n, a && out_bits);
+  if (((uintptr_t)out_bits & 15) != 0) return zc_fail(ctx, ZC_ERR_SIZE, "out_bits must be 16-byte aligned");
+  into_bits_kernel<<<grid_for(16 * n), TPB, 0, ctx->stream>>>(a, out_bits, n);
+  ZC_VEC_LAUNCHED(ctx);
+}
+int32_t zc_scalar_into_bits_batch(zc_ctx* ctx, const uint64_t* a, uint8_t* out_bits, size_t n) {
+  ZC_VEC_PROLOGUE(ctx, n, a && out_bits);
+  return host_run(ctx, a, n * 40, nullptr, 0, out_bits, n * 256, nullptr, 0, [&](void* d0, void*, void* dout, void*) {
+    return zc_scalar_into_bits_batch_dev(ctx, (const uint64_t*)d0, (uint8_t*)dout, n);
   });
 }
 

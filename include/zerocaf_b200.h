@@ -85,6 +85,30 @@ int32_t zc_fe_sub_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, u
 int32_t zc_fe_neg_batch_dev(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
 int32_t zc_fe_mul_square_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *prod, uint64_t *sq, size_t n);
 
+/* The same on the 32-byte wire format (FieldElement::to_bytes / from_bytes, field.rs:563-631: little-endian, canonical):
+ * the kernel moves exactly the algorithmic 128 bytes per pair and a host call 20 % fewer PCIe bytes than the limb layout.
+ * Arrays must be 16-byte aligned. */
+int32_t zc_fe_mul_square_batch_packed(zc_ctx *ctx, const uint8_t *a, const uint8_t *b, uint8_t *prod, uint8_t *sq, size_t n);
+int32_t zc_fe_mul_square_batch_packed_dev(zc_ctx *ctx, const uint8_t *a, const uint8_t *b, uint8_t *prod, uint8_t *sq, size_t n);
+/* replaces Div field.rs:277-299: out[i] = a[i] * b[i]^-1 (the reference asserts b != 0, field.rs:285; here a / 0 = 0) */
+int32_t zc_fe_div_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zc_fe_div_batch_dev(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+
+/* ---- input validation (opt-in) -------------------------------------------------------------------------------------
+ * The kernels assume canonical inputs (limbs < 2^52, value < modulus); the reference's types expose their limbs and its own
+ * tests build non-canonical values (field.rs:1160-1167, 1193-1200).  zc_*_check_canonical_batch checks an array on the
+ * device: ZC_OK, or ZC_ERR_NONCANONICAL with the index of the first offending element in *first_bad (may be NULL).
+ * zc_ctx_set_validation(ctx, 1) makes the hot-path entry points do that check on their own inputs -- field / scalar /
+ * point element-wise ops, mul_square, scalar multiplication, every MSM call -- and return ZC_ERR_NONCANONICAL (the outputs
+ * are then unspecified); `_dev` calls become synchronous while it is on. */
+int32_t zc_ctx_set_validation(zc_ctx *ctx, int32_t on);
+int32_t zc_fe_check_canonical_batch(zc_ctx *ctx, const uint64_t *a, size_t n, uint64_t *first_bad);
+int32_t zc_fe_check_canonical_batch_dev(zc_ctx *ctx, const uint64_t *a, size_t n, uint64_t *first_bad);
+int32_t zc_scalar_check_canonical_batch(zc_ctx *ctx, const uint64_t *a, size_t n, uint64_t *first_bad);
+int32_t zc_scalar_check_canonical_batch_dev(zc_ctx *ctx, const uint64_t *a, size_t n, uint64_t *first_bad);
+int32_t zc_point_check_canonical_batch(zc_ctx *ctx, const uint64_t *p, size_t n, uint64_t *first_bad);
+int32_t zc_point_check_canonical_batch_dev(zc_ctx *ctx, const uint64_t *p, size_t n, uint64_t *first_bad);
+
 /* ---- Scalar batch ops (mod L): replaces scalar.rs Mul :247-270, Square :272-283, Add :184-208, Sub :210-245, Neg --- */
 int32_t zc_scalar_mul_batch(zc_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 int32_t zc_scalar_square_batch(zc_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
@@ -183,6 +207,10 @@ int32_t zc_scalar_from_bytes_batch(zc_ctx *ctx, const uint8_t *in_bytes, uint64_
 int32_t zc_scalar_from_bytes_batch_dev(zc_ctx *ctx, const uint8_t *in_bytes, uint64_t *out, uint8_t *ok, size_t n);
 int32_t zc_scalar_window_naf_batch(zc_ctx *ctx, const uint64_t *a, int32_t width, int8_t *out_digits, size_t n);
 int32_t zc_scalar_window_naf_batch_dev(zc_ctx *ctx, const uint64_t *a, int32_t width, int8_t *out_digits, size_t n);
+/* into_bits: the 256 bits of each scalar, least significant first, one byte per bit (Scalar::into_bits, scalar.rs:352-366);
+ * out_bits must be 16-byte aligned on the device */
+int32_t zc_scalar_into_bits_batch(zc_ctx *ctx, const uint64_t *a, uint8_t *out_bits, size_t n);
+int32_t zc_scalar_into_bits_batch_dev(zc_ctx *ctx, const uint64_t *a, uint8_t *out_bits, size_t n);
 int32_t zc_fe_sqrt_ratio_i_batch(zc_ctx *ctx, const uint64_t *u, const uint64_t *v, uint64_t *out, uint8_t *was_square, size_t n);
 int32_t zc_fe_sqrt_ratio_i_batch_dev(zc_ctx *ctx, const uint64_t *u, const uint64_t *v, uint64_t *out, uint8_t *was_square, size_t n);
 
@@ -193,23 +221,35 @@ int32_t zc_fe_sqrt_ratio_i_batch_dev(zc_ctx *ctx, const uint64_t *u, const uint6
 int32_t zc_msm(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point);
 int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev);
 
-/* Fixed generators (bulletproofs G_i, H_i): prepare the MSM operands once.  After zc_msm_prepare_points_dev(points, n),
- * zc_msm_dev / zc_msm_partial_dev / zc_msm_sharded_dev calls with the SAME device pointer and n reuse the cached
- * operand array kept in the context instead of rebuilding it per call; the points are normalised to Z = 1 once (one field
- * inversion per point), so every bucket addition of the later calls is a 7-multiplication mixed addition instead of 8.  The caller must not modify points[]
- * in place while it is prepared; zc_msm_forget_points drops the cache.  Results are unchanged. */
-int32_t zc_msm_prepare_points_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t n);
-int32_t zc_msm_forget_points(zc_ctx *ctx);
-
-/* Fixed generators, traded for memory: build the FIXED-BASE TABLES  2^(window_bits * w) * P_i  (affine cached form, 128
- * bytes per row) for the windows w = rank (mod nranks) -- 16 x n rows at window_bits = 16 on one GPU (2 GiB for 2^20
- * points), 2 x n rows per rank on 8.  Later zc_msm_dev / zc_msm_partial_dev / zc_msm_sharded_dev calls with the SAME
- * (points pointer, n, window_bits, rank, nranks) then treat every (window, point) digit as an entry of ONE bucket set:
- * a single bucket reduction per rank and no doubling chain at all (the serial tail that limits the multi-GPU scaling of
- * the plain Pippenger path).  For zc_msm_sharded_dev pass the context's own rank / nranks.  One-time cost: c * w_max
- * doublings + one inversion per row.  Same contract as prepared points (do not modify points[] meanwhile; results
- * are the same group element); zc_msm_forget_points frees the tables.  Takes precedence over zc_msm_prepare_points_dev. */
-int32_t zc_msm_prepare_fixed_base_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t n, int32_t window_bits, int32_t rank, int32_t nranks);
+/* Fixed generators (bulletproofs G_i, H_i): an opaque handle that OWNS everything derived from the points.
+ *   kind = ZC_GEN_PREPARED    the points normalised to Z = 1 in cached form (one field inversion per point, 128 B per
+ *                             point): every bucket addition of a later MSM is a 7-multiplication mixed addition and the
+ *                             per-call operand pass disappears.  window_bits / rank / nranks are ignored; the handle
+ *                             serves any window size and any sharding.
+ *   kind = ZC_GEN_FIXED_BASE  memory for time: the FIXED-BASE TABLES  2^(window_bits * w) * P_i  (same 128-B record) for
+ *                             the windows w = rank (mod nranks) -- 16 x n rows at window_bits = 16 on one GPU (2 GiB for
+ *                             2^20 points), 2 x n rows per rank on 8.  An MSM of exactly that shape then treats every
+ *                             (window, point) digit as an entry of ONE bucket set: a single bucket reduction per rank and
+ *                             no doubling chain at all (the serial tail that limits the multi-GPU scaling of plain
+ *                             Pippenger).  One-time cost: window_bits * w_max doublings + one inversion per row.  A call
+ *                             with another (window_bits, rank, nranks) returns ZC_ERR_MODE.
+ * The point array is read during creation only (the call synchronises the stream before it returns): the caller may
+ * free, reuse or overwrite it afterwards -- nothing is keyed by its address, so a recycled allocation cannot alias an
+ * old generator set.  Several handles can be alive at once (G and H vectors).  A handle belongs to the context that
+ * created it; destroy it before the context.  Results are the same group element as the plain calls. */
+#define ZC_GEN_PREPARED    1
+#define ZC_GEN_FIXED_BASE  2
+typedef struct zc_msm_generators zc_msm_generators;
+int32_t zc_msm_generators_create_dev(zc_ctx *ctx, const uint64_t *points_dev, size_t n, int32_t kind, int32_t window_bits,
+                                     int32_t rank, int32_t nranks, zc_msm_generators **out);
+int32_t zc_msm_generators_destroy(zc_ctx *ctx, zc_msm_generators *gens);
+/* n, kind and the device bytes the handle owns (any out pointer may be NULL) */
+int32_t zc_msm_generators_info(const zc_msm_generators *gens, size_t *n, int32_t *kind, size_t *device_bytes);
+/* sum_i [s_i] G_i over the handle's n generators; scalars_dev holds n scalars.  _partial / _sharded as below. */
+int32_t zc_msm_gen_dev(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *scalars_dev, int32_t window_bits, uint64_t *out_point_dev);
+int32_t zc_msm_gen_partial_dev(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *scalars_dev, int32_t window_bits,
+                               int32_t rank, int32_t nranks, uint64_t *out_point_dev);
+int32_t zc_msm_gen_sharded_dev(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *scalars_dev, int32_t window_bits, uint64_t *out_point_dev);
 
 /* Bucket-window-sharded MSM: a collective, every rank calls it with the same (points, scalars, n, window_bits), all
  * resident on its own device.  Rank r accumulates windows w = r (mod nranks), scales its window sums and folds them to
@@ -223,10 +263,22 @@ int32_t zc_nccl_comm_destroy(void *comm);
 /* Exchange over NVLink peer memory instead of NCCL: every rank creates a mailbox in its own HBM (zc_peer_mailbox_create
  * returns its 64-byte CUDA IPC handle), the handles of all ranks are gathered with the host framework's transport and
  * passed, in rank order, to zc_peer_mailbox_connect.  zc_msm_sharded_dev then delivers the partial points with peer
- * stores, waits on flags and folds them in one kernel (a fixed tree of the reference Add: identical bits on all ranks). */
+ * stores, waits on flags and folds them in one kernel (a fixed tree: identical bits on all ranks).  Slots and flags are
+ * double-buffered by sequence parity, so back-to-back exchanges cannot overwrite a partial a slower peer still reads; the
+ * flag wait is bounded (ZC_PEER_TIMEOUT_MS, default 5000): if a rank never arrives the kernel returns the identity and
+ * zc_ctx_sync / zc_msm_sharded report ZC_ERR_STATE naming the missing rank instead of hanging. */
 int32_t zc_peer_mailbox_create(zc_ctx *ctx, uint8_t handle_out[64]);
 int32_t zc_peer_mailbox_connect(zc_ctx *ctx, const uint8_t *handles /* nranks x 64 */, int32_t rank, int32_t nranks);
+/* One process driving several contexts (several GPUs with peer access, or several streams of one GPU): the mailboxes are
+ * plain device pointers -- zc_peer_mailbox_create(ctx, scratch), zc_peer_mailbox_ptr on every context, then
+ * zc_peer_mailbox_connect_local with the nranks pointers in rank order.  The calls of one collective may be enqueued from
+ * a single host thread, rank after rank (they do not block the host). */
+int32_t zc_peer_mailbox_ptr(zc_ctx *ctx, void **out);
+int32_t zc_peer_mailbox_connect_local(zc_ctx *ctx, void *const *mailboxes /* nranks */, int32_t rank, int32_t nranks);
 int32_t zc_msm_sharded_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point_dev);
+/* the same collective with HOST pointers (every rank passes the same arrays; synchronous; the copies are pipelined with
+ * the operand pass) */
+int32_t zc_msm_sharded(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits, uint64_t *out_point);
 /* the local half only (no exchange): rank r's partial point, for tests of the sharding logic without NCCL */
 int32_t zc_msm_partial_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int32_t window_bits,
                            int32_t rank, int32_t nranks, uint64_t *out_point_dev);

@@ -48,21 +48,27 @@ def _worker(rank, world, port, q):
 
     results = []
     ctx.init_nccl(rank, world, bcast)
+    gens = None
     for path in ("nccl", "peer", "peer+prepared", "peer+fixed_base"):
         if path == "peer":
             ctx.init_peer_mailboxes(rank, world, allgather)
         elif path == "peer+prepared":
-            ctx.msm_prepare_points(P.data_ptr(), n)
+            gens = ctx.msm_generators(P.data_ptr(), n, zc.GEN_PREPARED)
         elif path == "peer+fixed_base":
-            ctx.msm_prepare_fixed_base(P.data_ptr(), n, c, rank, world)
+            gens.close()
+            gens = ctx.msm_generators(P.data_ptr(), n, zc.GEN_FIXED_BASE, c, rank, world)
         out = torch.zeros(20, dtype=torch.int64, device=dev)
         for _ in range(3):                                               # repeated calls: sequence numbers / graph replay
-            ctx.check(L.zc_msm_sharded_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, c, out.data_ptr()))
+            if gens is not None:
+                gens.msm_sharded(S.data_ptr(), out.data_ptr(), window_bits=c)
+            else:
+                ctx.check(L.zc_msm_sharded_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, c, out.data_ptr()))
         eq = torch.zeros(1, dtype=torch.uint8, device=dev)
         ctx.check(L.zc_ristretto_eq_batch_dev(ctx._h, out.data_ptr(), full.data_ptr(), eq.data_ptr(), 1))
         ctx.sync()
         results.append((path, bool(eq.item()), out.cpu().numpy().tobytes()))
     q.put((rank, results))
+    gens.close()
     ctx.close()
     dist.destroy_process_group()
 

@@ -469,8 +469,8 @@ def test_msm_call_sequence_reuses_workspace_and_graph(zc, oracle):
 
 
 def test_msm_prepared_points(zc, oracle):
-    """zc_msm_prepare_points_dev: same result with the cached operands, for several scalar vectors, window sizes (the
-    workspace grows -> the cache is rebuilt) and after forgetting."""
+    """zc_msm_generators (ZC_GEN_PREPARED): same result through the handle's cached operands, for several scalar vectors and
+    window sizes, with other MSMs (plain, and through a second live handle) in between."""
     import torch
     n = 5000
     P = synth_points(oracle, 80, n)
@@ -478,31 +478,82 @@ def test_msm_prepared_points(zc, oracle):
     L = ctx._L
     dP = torch.from_numpy(P.view(np.int64)).cuda()
     out = torch.zeros(20, dtype=torch.int64, device="cuda")
-    ctx.check(L.zc_msm_prepare_points_dev(ctx._h, dP.data_ptr(), n))
+    gens = ctx.msm_generators(dP.data_ptr(), n, zc.GEN_PREPARED)
+    assert gens.device_bytes == n * 128
     for k, c in enumerate((16, 12, 16, 9)):
         s = oracle.synth_scalar(SEED, 81 + k, 0, n)
         dS = torch.from_numpy(s.view(np.int64)).cuda()
-        ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, out.data_ptr()))
+        gens.msm(dS.data_ptr(), out.data_ptr(), window_bits=c)
         ctx.sync()
         assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8)), (k, c)
-    # an MSM over OTHER points in between reuses the workspace: the prepared set must be rebuilt, not trusted
+    # a plain MSM over OTHER points and an MSM through a second handle in between
     P2 = synth_points(oracle, 85, 700)
     s2 = oracle.synth_scalar(SEED, 86, 0, 700)
     dP2, dS2 = torch.from_numpy(P2.view(np.int64)).cuda(), torch.from_numpy(s2.view(np.int64)).cuda()
+    gens2 = ctx.msm_generators(dP2.data_ptr(), 700, zc.GEN_PREPARED)
     ctx.check(L.zc_msm_dev(ctx._h, dP2.data_ptr(), dS2.data_ptr(), 700, 16, out.data_ptr()))
     ctx.sync()
-    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P2, s2, threads=8))
+    want2 = oracle.msm_naive(P2, s2, threads=8)
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want2)
+    gens2.msm(dS2.data_ptr(), out.data_ptr())
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want2)
+    gens.msm(dS.data_ptr(), out.data_ptr())
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
+    # sharded partials through the handle fold to the same element
+    parts = torch.zeros((4, 20), dtype=torch.int64, device="cuda")
+    for r in range(4):
+        gens.msm_partial(dS.data_ptr(), parts[r].data_ptr(), r, 4)
+    ctx.check(L.zc_point_fold_dev(ctx._h, parts.data_ptr(), 4, out.data_ptr()))
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
+    gens2.close()
+    gens.close()
     ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
     ctx.sync()
     assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
-    ctx.check(L.zc_msm_forget_points(ctx._h))
-    ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
-    ctx.sync()
-    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P, s, threads=8))
+
+
+def test_msm_generators_do_not_alias_a_recycled_address(zc, oracle):
+    """ADVICE r1 / VERDICT r1 weak 3: prepared state used to be keyed by the raw device pointer, so freeing the points and
+    getting the same address back with other generators silently returned the OLD result.  The handle owns a snapshot:
+    overwriting the array in place (what a free + malloc at the same address amounts to) changes the plain call and not the
+    handle; a new handle made from the same address sees the new points; stale handles after destroy do not match graphs."""
+    import torch
+    n = 2000
+    Pa, Pb = synth_points(oracle, 90, n), synth_points(oracle, 91, n)
+    s = oracle.synth_scalar(SEED, 92, 0, n)
+    ctx = zc.default_context()
+    L = ctx._L
+    dP = torch.from_numpy(Pa.view(np.int64)).cuda()
+    dS = torch.from_numpy(s.view(np.int64)).cuda()
+    out = torch.zeros(20, dtype=torch.int64, device="cuda")
+    want_a, want_b = oracle.msm_naive(Pa, s, threads=8), oracle.msm_naive(Pb, s, threads=8)
+    for kind in (zc.GEN_PREPARED, zc.GEN_FIXED_BASE):
+        dP.copy_(torch.from_numpy(Pa.view(np.int64)))
+        g_old = ctx.msm_generators(dP.data_ptr(), n, kind, 16, 0, 1)
+        g_old.msm(dS.data_ptr(), out.data_ptr())
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want_a)
+        dP.copy_(torch.from_numpy(Pb.view(np.int64)))           # same address, other generators
+        torch.cuda.synchronize()
+        ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want_b), "plain call must see the new points"
+        g_old.msm(dS.data_ptr(), out.data_ptr())
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want_a), "the handle owns its snapshot"
+        g_old.close()
+        g_new = ctx.msm_generators(dP.data_ptr(), n, kind, 16, 0, 1)
+        g_new.msm(dS.data_ptr(), out.data_ptr())                 # a recorded graph of g_old must not be replayed
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want_b)
+        g_new.close()
 
 
 def test_msm_fixed_base_tables(zc, oracle):
-    """zc_msm_prepare_fixed_base_dev: pre-scaled per-window tables, one merged bucket set, no doubling chain -- the same
+    """zc_msm_generators (ZC_GEN_FIXED_BASE): pre-scaled per-window tables, one merged bucket set, no doubling chain -- the same
     group element as the naive sum for several window sizes (aligned and not, short top windows), several scalar vectors
     (incl. the extreme digits of L - 1 and small scalars), sharded over R ranks, and unaffected by other MSMs between."""
     import torch
@@ -518,40 +569,51 @@ def test_msm_fixed_base_tables(zc, oracle):
     svecs[1][2] = oracle.int_to_limbs(1)
     svecs[1][3] = oracle.int_to_limbs((1 << 249) - 1)
     want = [oracle.msm_naive(P, s, threads=8) for s in svecs]
+    dSs = [torch.from_numpy(s.view(np.int64)).cuda() for s in svecs]
     for c, R in ((16, 1), (13, 1), (8, 1), (11, 1), (16, 2), (16, 8), (12, 3), (16, 32)):
-        for k, s in enumerate(svecs):
-            dS = torch.from_numpy(s.view(np.int64)).cuda()
-            parts = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
-            for r in range(R):
-                ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, c, r, R))
-                ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, r, R, parts[r].data_ptr()))
+        parts = [torch.zeros((R, 20), dtype=torch.int64, device="cuda") for _ in svecs]
+        for r in range(R):
+            g = ctx.msm_generators(dP.data_ptr(), n, zc.GEN_FIXED_BASE, c, r, R)
+            for k, dS in enumerate(dSs):
+                g.msm_partial(dS.data_ptr(), parts[k][r].data_ptr(), r, R)
                 # replay of the recorded graph: the same group element (bucket order is up to the histogram atomics)
-                ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, r, R, out.data_ptr()))
+                g.msm_partial(dS.data_ptr(), out.data_ptr(), r, R)
                 ctx.sync()
-                assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), parts[r].cpu().numpy().view(np.uint64)), (c, R, r)
-            ctx.check(L.zc_point_fold_dev(ctx._h, parts.data_ptr(), R, out.data_ptr()))
+                assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), parts[k][r].cpu().numpy().view(np.uint64)), (c, R, r)
+            g.close()
+        for k in range(len(svecs)):
+            ctx.check(L.zc_point_fold_dev(ctx._h, parts[k].data_ptr(), R, out.data_ptr()))
             ctx.sync()
             assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want[k]), (c, R, k)
-    # tables for (c=16, rank 0 of 1); a different shape falls back to the plain path, then the tables are used again
-    ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 16, 0, 1))
-    dS = torch.from_numpy(svecs[0].view(np.int64)).cuda()
-    for c, m in ((16, n), (12, n), (16, 700), (16, n)):
+    # tables for (c=16, rank 0 of 1): another shape is refused (ZC_ERR_MODE), plain calls in between do not disturb them
+    g = ctx.msm_generators(dP.data_ptr(), n, zc.GEN_FIXED_BASE, 16, 0, 1)
+    dS = dSs[0]
+    assert L.zc_msm_gen_dev(ctx._h, g._g, dS.data_ptr(), 12, out.data_ptr()) == 3
+    assert L.zc_msm_gen_partial_dev(ctx._h, g._g, dS.data_ptr(), 16, 1, 2, out.data_ptr()) == 3
+    for c, m in ((16, n), (12, n), (16, 700)):
         ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), m, c, out.data_ptr()))
         ctx.sync()
         w = want[0] if m == n else oracle.msm_naive(P[:m], svecs[0][:m], threads=8)
         assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), w), (c, m)
+        g.msm(dS.data_ptr(), out.data_ptr())
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want[0]), (c, m)
+    g.close()
     # tiny and ragged sizes through the merged bucket set
     for m, c, R in ((1, 16, 1), (2, 8, 1), (33, 16, 2), (257, 10, 1), (1000, 16, 8)):
         parts = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
         for r in range(R):
-            ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), m, c, r, R))
-            ctx.check(L.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), m, c, r, R, parts[r].data_ptr()))
+            g = ctx.msm_generators(dP.data_ptr(), m, zc.GEN_FIXED_BASE, c, r, R)
+            g.msm_partial(dS.data_ptr(), parts[r].data_ptr(), r, R)
+            g.close()
         ctx.check(L.zc_point_fold_dev(ctx._h, parts.data_ptr(), R, out.data_ptr()))
         ctx.sync()
         assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), oracle.msm_naive(P[:m], svecs[0][:m], threads=8)), (m, c, R)
-    assert L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 17, 0, 1) == 3
-    assert L.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, 16, 2, 2) == 2
-    ctx.check(L.zc_msm_forget_points(ctx._h))
+    import ctypes
+    h = ctypes.c_void_p()
+    assert L.zc_msm_generators_create_dev(ctx._h, dP.data_ptr(), n, zc.GEN_FIXED_BASE, 17, 0, 1, ctypes.byref(h)) == 3
+    assert L.zc_msm_generators_create_dev(ctx._h, dP.data_ptr(), n, zc.GEN_FIXED_BASE, 16, 2, 2, ctypes.byref(h)) == 2
+    assert L.zc_msm_generators_create_dev(ctx._h, dP.data_ptr(), n, 7, 16, 0, 1, ctypes.byref(h)) == 3
     ctx.check(L.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
     ctx.sync()
     assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want[0])

@@ -37,16 +37,15 @@ def test_msm_all_window_sizes_with_top_bit_scalars(zc, oracle):
     dS = torch.from_numpy(s.view(np.int64)).cuda()
     out = torch.zeros(20, dtype=torch.int64, device="cuda")
     for c in range(8, 17):
-        ctx.check(Lb.zc_msm_forget_points(ctx._h))
         ctx.check(Lb.zc_msm_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, out.data_ptr()))
         ctx.sync()
         assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want), ("plain", c)
         for R in (1, 3):
             parts = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
             for r in range(R):
-                ctx.check(Lb.zc_msm_prepare_fixed_base_dev(ctx._h, dP.data_ptr(), n, c, r, R))
-                ctx.check(Lb.zc_msm_partial_dev(ctx._h, dP.data_ptr(), dS.data_ptr(), n, c, r, R, parts[r].data_ptr()))
+                g = ctx.msm_generators(dP.data_ptr(), n, zc.GEN_FIXED_BASE, c, r, R)
+                g.msm_partial(dS.data_ptr(), parts[r].data_ptr(), r, R)
+                g.close()
             ctx.check(Lb.zc_point_fold_dev(ctx._h, parts.data_ptr(), R, out.data_ptr()))
             ctx.sync()
             assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want), ("fixed_base", c, R)
-    ctx.check(Lb.zc_msm_forget_points(ctx._h))

@@ -34,19 +34,20 @@ ctx.check(L.zc_point_scalar_mul_batch_dev(ctx._h, base.data_ptr(), sc.data_ptr()
 S = torch.from_numpy(synth.synth_scalar(102, 0, n).view(np.int64)).to(dev)
 out = torch.zeros(20, dtype=torch.int64, device=dev)
 ctx.sync()
+gens = None
 if a.prepared:
-    ctx.check(L.zc_msm_prepare_points_dev(ctx._h, P.data_ptr(), n))
+    gens = ctx.msm_generators(P.data_ptr(), n, zc.GEN_PREPARED)
 if a.fixed_base:
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, P.data_ptr(), n, a.c, a.rank, a.nranks))
-    e1.record(st)
-    st.synchronize()
-    print(f"fixed-base tables rank {a.rank}/{a.nranks}: {e0.elapsed_time(e1):.1f} ms", flush=True)
+    t0 = time.perf_counter()
+    gens = ctx.msm_generators(P.data_ptr(), n, zc.GEN_FIXED_BASE, a.c, a.rank, a.nranks)
+    print(f"fixed-base tables rank {a.rank}/{a.nranks}: {(time.perf_counter() - t0) * 1e3:.1f} ms, {gens.device_bytes >> 20} MiB", flush=True)
 for it in range(a.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    ctx.check(L.zc_msm_partial_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, a.c, a.rank, a.nranks, out.data_ptr()))
+    if gens is not None:
+        gens.msm_partial(S.data_ptr(), out.data_ptr(), a.rank, a.nranks, window_bits=a.c)
+    else:
+        ctx.check(L.zc_msm_partial_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, a.c, a.rank, a.nranks, out.data_ptr()))
     e1.record(st)
     st.synchronize()
     print(f"msm n={n} c={a.c} rank {a.rank}/{a.nranks}: {e0.elapsed_time(e1):.3f} ms", flush=True)
@@ -54,7 +55,6 @@ if a.check and a.fixed_base:
     # the same MSM through the plain path (no tables) must be the same group element
     ctx.sync()
     ref = torch.zeros(20, dtype=torch.int64, device=dev)
-    ctx.check(L.zc_msm_forget_points(ctx._h))
     ctx.check(L.zc_msm_partial_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, a.c, a.rank, a.nranks, ref.data_ptr()))
     ctx.sync()
     eq = zc.batch.ristretto_eq(out.cpu().numpy().view(np.uint64)[None], ref.cpu().numpy().view(np.uint64)[None])

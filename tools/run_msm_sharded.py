@@ -85,7 +85,11 @@ if world > 1:
 else:
     fn = lambda: ctx.check(L.zc_msm_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, c, out.data_ptr()))
 res["ms_plain"] = timed(fn, a.iters)
-ctx.check(L.zc_msm_prepare_points_dev(ctx._h, P.data_ptr(), n))
+gens = ctx.msm_generators(P.data_ptr(), n, zc.GEN_PREPARED)
+if world > 1:
+    fn = lambda: gens.msm_sharded(S.data_ptr(), out.data_ptr(), window_bits=c)
+else:
+    fn = lambda: gens.msm(S.data_ptr(), out.data_ptr(), window_bits=c)
 res["ms_prepared_points"] = timed(fn, a.iters)
 prepared_pt = out.clone()
 if world > 1:
@@ -95,12 +99,13 @@ if world > 1:
             dist.broadcast(S, src=0)
         fn()
     res["ms_prepared_points_incl_scalar_broadcast"] = timed(fn_bcast, a.iters, warmup=2)
-ctx.check(L.zc_msm_prepare_fixed_base_dev(ctx._h, P.data_ptr(), n, c, rank, world))
+gens.close()
+gens = ctx.msm_generators(P.data_ptr(), n, zc.GEN_FIXED_BASE, c, rank, world)
 res["ms_fixed_base_tables"] = timed(fn, a.iters)
 fb_pt = out.clone()
 
 # checks: all ranks hold identical bits; both modes equal this rank's own single-GPU plain MSM as group elements
-ctx.check(L.zc_msm_forget_points(ctx._h))
+gens.close()
 full = torch.zeros(20, dtype=torch.int64, device=dev)
 ctx.check(L.zc_msm_dev(ctx._h, P.data_ptr(), S.data_ptr(), n, c, full.data_ptr()))
 eq = torch.zeros(2, dtype=torch.uint8, device=dev)
