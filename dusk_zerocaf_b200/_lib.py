@@ -102,6 +102,7 @@ def lib():
         for kind in ("fe", "scalar", "point"):
             getattr(L, f"zc_{kind}_check_canonical_batch{suf}").argtypes = [vp, vp, sz, u64p]
     L.zc_ctx_set_validation.argtypes = [vp, i32]
+    L.zc_msm_plan_query.argtypes = [i32, i32, i32, ctypes.POINTER(i32)]
     L.zc_msm_generators_create_dev.argtypes = [vp, vp, sz, i32, i32, i32, i32, ctypes.POINTER(vp)]
     L.zc_msm_generators_destroy.argtypes = [vp, vp]
     L.zc_msm_generators_info.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(i32), ctypes.POINTER(sz)]

@@ -116,8 +116,8 @@ static inline int32_t zc_scratch(zc_ctx *ctx, int slot, size_t bytes, void **out
 int32_t zc_peer_exchange_fold(zc_ctx *ctx, const uint64_t *partial, uint64_t *out);
 int32_t zc_peer_check_error(zc_ctx *ctx);
 // implemented in zc_kernels.cu (extern "C", not in the public header): enqueue a canonical-input check (kind 1 field, 2 scalar, 3 point) / read the verdict
-extern "C" int32_t zc_validate_dev(zc_ctx *ctx, int32_t kind, const uint64_t *a, size_t n, size_t base);
-extern "C" int32_t zc_validate_finish(zc_ctx *ctx, int32_t elems_per_unit);
+int32_t zc_validate_dev(zc_ctx *ctx, int32_t kind, const uint64_t *a, size_t n, size_t base);
+int32_t zc_validate_finish(zc_ctx *ctx, int32_t elems_per_unit);
 // implemented in zc_msm.cu
 int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *points, const uint64_t *scalars, size_t n,
                    int32_t window_bits, int32_t rank, int32_t nranks, bool exchange, uint64_t *out_point_dev);

@@ -781,11 +781,6 @@ int32_t zc_ctx_set_validation(zc_ctx* ctx, int32_t on) {
   ctx->validate = on != 0;
   return ZC_OK;
 }
-int32_t zc_validate_dev(zc_ctx* ctx, int32_t kind, const uint64_t* a, size_t n, size_t base) {   // internal (zc_msm.cu): 1 field, 2 scalar, 3 point
-  if (kind == 2) return validation_enqueue<ModL>(ctx, a, n, base);
-  return validation_enqueue<ModP>(ctx, a, kind == 3 ? 4 * n : n, kind == 3 ? 4 * base : base);
-}
-int32_t zc_validate_finish(zc_ctx* ctx, int32_t elems_per_unit) { return validation_finish(ctx, elems_per_unit, nullptr); }
 
 #define ZC_DEFINE_CHECK(NAME, MOD, STRIDE_LIMBS)                                                                     \
   int32_t NAME##_dev(zc_ctx* ctx, const uint64_t* a, size_t n, uint64_t* first_bad) {                               \
@@ -814,3 +809,10 @@ ZC_DEFINE_CHECK(zc_scalar_check_canonical_batch, ModL, 5)
 ZC_DEFINE_CHECK(zc_point_check_canonical_batch, ModP, 20)
 
 }  // extern "C"
+
+// internal (zc_msm.cu), C++ linkage: enqueue a canonical-input check (kind 1 field, 2 scalar, 3 point) / read the verdict
+int32_t zc_validate_dev(zc_ctx* ctx, int32_t kind, const uint64_t* a, size_t n, size_t base) {   // internal (zc_msm.cu): 1 field, 2 scalar, 3 point
+  if (kind == 2) return validation_enqueue<ModL>(ctx, a, n, base);
+  return validation_enqueue<ModP>(ctx, a, kind == 3 ? 4 * n : n, kind == 3 ? 4 * base : base);
+}
+int32_t zc_validate_finish(zc_ctx* ctx, int32_t elems_per_unit) { return validation_finish(ctx, elems_per_unit, nullptr); }

@@ -96,6 +96,16 @@ __host__ __device__ constexpr int merged_spread_bits(int c, int w) {
   return (250 - c * w > 0 && short_window_sub_bits(c, w) > 1) ? short_window_sub_bits(c, w) - 1 : 0;
 }
 
+// Window ownership of the bucket-window sharding: boustrophedon over the ranks (windows 0..R-1 go to ranks 0..R-1, windows
+// R..2R-1 to ranks R-1..0, and so on).  A rank's partial sum costs  reduce(top window) + c (w_top - w_low) doublings  while its
+// lower windows accumulate, then  reduce(lowest window) + c w_low doublings  after the last accumulation: pairing the
+// highest window with the lowest one keeps both serial chains short on every rank (w mod R put windows 7 and 15 on one
+// rank at R = 8: 128 + 112 doublings; now (7, 8): 16 + 112, and (0, 15): 240 + 0 with the long chain hidden under the
+// low window's accumulation).
+__host__ __device__ constexpr int window_owner(int w, int nranks) {
+  return ((w / nranks) & 1) ? nranks - 1 - (w % nranks) : (w % nranks);
+}
+
 // Which of this rank's tasks (local index tl, or -1) takes window w, and for which point range [p0, p1).  A task is a
 // window (all points) today; the range exists so that a window can be split by points between ranks.
 // merged != 0 (fixed-base tables): all of the rank's windows share ONE set of buckets -- the table entry of (window, point)
@@ -857,14 +867,14 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
   if (n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "n exceeds 2^31 - 1");
   const int nwin = (256 + c - 1) / c;
   const int nb = 1 << (c - 1);
-  // Tasks of this rank, ascending by window: the windows w = rank (mod nranks) over all n points.  (A task may also be a
+  // Tasks of this rank, ascending by window: the windows it owns (window_owner) over all n points.  (A task may also be a
   // point range of a window -- msm_digits_kernel honours [p0, p1).  Splitting the low windows between rank pairs, so that
   // no rank's last window needs more than c (nranks/2 - 1) doublings, was measured at 8 ranks and did not pay: the third
   // bucket reduction per rank costs what the shorter chain saves.)
   struct Task { int w; uint32_t p0, p1; };
   Task tasks[MAX_WINDOWS];
   int nwl = 0;
-  for (int w = 0; w < nwin; w++) if (w % nranks == rank) tasks[nwl++] = {w, 0u, (uint32_t)n};
+  for (int w = 0; w < nwin; w++) if (window_owner(w, nranks) == rank) tasks[nwl++] = {w, 0u, (uint32_t)n};
   WinMap wmap;
   for (int w = 0; w < MAX_WINDOWS; w++) { wmap.tl[w] = -1; wmap.p0[w] = 0; wmap.p1[w] = 0; }
   for (int t = 0; t < nwl; t++) { wmap.tl[tasks[t].w] = (int16_t)t; wmap.p0[tasks[t].w] = tasks[t].p0; wmap.p1[tasks[t].w] = tasks[t].p1; }
@@ -1105,7 +1115,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         // stage 1 runs ON the main stream, ahead of the next accumulation.  ZC_MSM_SEQ_STAGE1 = 0 / 1 forces it.
         static const int seq_env = getenv("ZC_MSM_SEQ_STAGE1") ? atoi(getenv("ZC_MSM_SEQ_STAGE1")) : -1;
         const int chain_after = (g == ngroups - 1) ? 0 : c * (tasks[lo].w - tasks[lo - 1].w);   // doublings this group's sums wait for
-        const bool seq1 = (g < ngroups - 1) && (seq_env >= 0 ? seq_env != 0 : (nranks > 1 && chain_after >= 96));
+        // Worth it when this group's chain would otherwise end after the LAST group's reduction + final scaling are ready:
+        // in-line stage 1 delays the later accumulations by ~50 us and brings this group's sums forward by ~100 us.
+        const int post_all = c * tasks[0].w;                     // doublings after the last group (the rank's lowest window)
+        const bool seq1 = (g < ngroups - 1) && (seq_env >= 0 ? seq_env != 0 : (nranks > 1 && g == 0 && chain_after - post_all > 118));
         cudaStream_t s1 = seq1 ? st : side;
         const int s1id = seq1 ? 0 : 1;
         if (!seq1) {
@@ -1191,18 +1204,32 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       ZC_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)ctx->msm_graph_exec, st));
       ctx->launches += ctx->msm_graph_launches;
     } else {
-      if (ctx->msm_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec); ctx->msm_graph_exec = nullptr; }
       ZC_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       int32_t rc = enqueue();
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
       ZC_CUDA(ctx, e);
-      cudaGraphExec_t exec = nullptr;
-      e = cudaGraphInstantiate(&exec, graph, 0);
+      // New arguments, same shape (new scalars / points / output buffer -- the common case): retarget the instantiated graph
+      // in place.  cudaGraphExecUpdate touches no device allocation; destroying and re-instantiating an executable graph
+      // frees device memory, which synchronises the DEVICE -- a stall per call, and a deadlock (until the exchange's deadline)
+      // when another rank of the same process is already spinning in its exchange kernel.
+      cudaGraphExec_t exec = (cudaGraphExec_t)ctx->msm_graph_exec;
+      bool updated = false;
+      if (exec && ctx->msm_key.n == key.n && ctx->msm_key.c == key.c && ctx->msm_key.rank == key.rank && ctx->msm_key.nranks == key.nranks &&
+          ctx->msm_key.mode == key.mode && ctx->msm_key.ws == key.ws) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(exec, graph, &info) == cudaSuccess) updated = true;
+        else cudaGetLastError();                                // topology differs after all: instantiate below
+      }
+      if (!updated) {
+        if (exec) { cudaGraphExecDestroy(exec); ctx->msm_graph_exec = nullptr; }
+        exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        if (e != cudaSuccess) { cudaGraphDestroy(graph); ZC_CUDA(ctx, e); }
+        ctx->msm_graph_exec = exec;
+      }
       cudaGraphDestroy(graph);
-      ZC_CUDA(ctx, e);
-      ctx->msm_graph_exec = exec;
       ctx->msm_key = key;
       ctx->msm_graph_launches = nlaunch;
       ZC_CUDA(ctx, cudaGraphLaunch(exec, st));
@@ -1233,6 +1260,20 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
 
 extern "C" {
 
+// The plan rules as host functions (no device needed): which rank owns a window and how a short window is spread.  The
+// Python / C++ mirrors and a caller that pre-extracts one rank's digits ask the library instead of restating the rules.
+int32_t zc_msm_plan_query(int32_t window_bits, int32_t window, int32_t nranks, int32_t out[4]) {
+  if (!out) return ZC_ERR_NULL;
+  if (window_bits < 8 || window_bits > 16) return ZC_ERR_MODE;
+  const int nwin = (256 + window_bits - 1) / window_bits;
+  if (window < 0 || window >= nwin || nranks < 1) return ZC_ERR_SIZE;
+  out[0] = window_owner(window, nranks);
+  out[1] = short_window_sub_bits(window_bits, window);
+  out[2] = merged_spread_bits(window_bits, window);
+  out[3] = window_bits * window - merged_spread_bits(window_bits, window);      // a fixed-base table row of this window is 2^out[3] P_i
+  return ZC_OK;
+}
+
 // ---- fixed generators: an opaque handle that owns everything derived from the points ---------------------------------
 int32_t zc_msm_generators_create_dev(zc_ctx *ctx, const uint64_t *points, size_t n, int32_t kind, int32_t window_bits,
                                      int32_t rank, int32_t nranks, zc_msm_generators **out) {
@@ -1250,7 +1291,7 @@ int32_t zc_msm_generators_create_dev(zc_ctx *ctx, const uint64_t *points, size_t
     if (c < 8 || c > 16) return zc_fail(ctx, ZC_ERR_MODE, "window_bits must be in 8..16");
     if (nranks < 1 || rank < 0 || rank >= nranks) return zc_fail(ctx, ZC_ERR_SIZE, "bad rank / nranks");
     const int nwin = (256 + c - 1) / c;
-    for (int w = 0; w < nwin; w++) if (w % nranks == rank) win.w[win.nwl++] = (int16_t)w;
+    for (int w = 0; w < nwin; w++) if (window_owner(w, nranks) == rank) win.w[win.nwl++] = (int16_t)w;
     for (int t = win.nwl; t < MAX_WINDOWS; t++) win.w[t] = 0;
     if ((size_t)win.nwl * n > ((size_t)1 << 31) - 1) return zc_fail(ctx, ZC_ERR_SIZE, "windows x points exceeds 2^31 - 1");
   }

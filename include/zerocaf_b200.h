@@ -227,7 +227,7 @@ int32_t zc_msm_dev(zc_ctx *ctx, const uint64_t *points, const uint64_t *scalars,
  *                             per-call operand pass disappears.  window_bits / rank / nranks are ignored; the handle
  *                             serves any window size and any sharding.
  *   kind = ZC_GEN_FIXED_BASE  memory for time: the FIXED-BASE TABLES  2^(window_bits * w) * P_i  (same 128-B record) for
- *                             the windows w = rank (mod nranks) -- 16 x n rows at window_bits = 16 on one GPU (2 GiB for
+ *                             the windows the rank owns (zc_msm_plan_query) -- 16 x n rows at window_bits = 16 on one GPU (2 GiB for
  *                             2^20 points), 2 x n rows per rank on 8.  An MSM of exactly that shape then treats every
  *                             (window, point) digit as an entry of ONE bucket set: a single bucket reduction per rank and
  *                             no doubling chain at all (the serial tail that limits the multi-GPU scaling of plain
@@ -251,8 +251,14 @@ int32_t zc_msm_gen_partial_dev(zc_ctx *ctx, const zc_msm_generators *gens, const
                                int32_t rank, int32_t nranks, uint64_t *out_point_dev);
 int32_t zc_msm_gen_sharded_dev(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *scalars_dev, int32_t window_bits, uint64_t *out_point_dev);
 
+/* The sharding plan as a host function (no device needed): out[0] = the rank that owns `window` among nranks (boustrophedon:
+ * windows 0..R-1 -> ranks 0..R-1, R..2R-1 -> ranks R-1..0, ... so the rank with the highest window also has the lowest),
+ * out[1] = sub-bucket bits of a short top window (plain path), out[2] = spread bits of a short window in the fixed-base
+ * path, out[3] = s such that a fixed-base table row of this window is 2^s P_i. */
+int32_t zc_msm_plan_query(int32_t window_bits, int32_t window, int32_t nranks, int32_t out[4]);
+
 /* Bucket-window-sharded MSM: a collective, every rank calls it with the same (points, scalars, n, window_bits), all
- * resident on its own device.  Rank r accumulates windows w = r (mod nranks), scales its window sums and folds them to
+ * resident on its own device.  Rank r accumulates the windows it owns (zc_msm_plan_query), scales its window sums and folds them to
  * one partial point; the partial points are exchanged ONCE -- over NVLink peer memory (zc_peer_mailbox_*) or with one
  * ncclAllGather on the context's stream -- and folded in a fixed order on every rank, so all ranks return identical bits.  `nccl_comm` is an ncclComm_t created by the caller
  * (e.g. from an ncclUniqueId distributed with torch.distributed); libnccl is resolved at run time with dlopen. */

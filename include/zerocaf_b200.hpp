@@ -89,6 +89,11 @@ struct FieldElement {
   friend FieldElement operator+(const FieldElement& a, const FieldElement& b) { FieldElement r; Gpu::instance().check(zc_fe_add_batch(Gpu::instance().ctx(), a.l, b.l, r.l, 1)); return r; }
   friend FieldElement operator-(const FieldElement& a, const FieldElement& b) { FieldElement r; Gpu::instance().check(zc_fe_sub_batch(Gpu::instance().ctx(), a.l, b.l, r.l, 1)); return r; }
   friend FieldElement operator*(const FieldElement& a, const FieldElement& b) { FieldElement r; Gpu::instance().check(zc_fe_mul_batch(Gpu::instance().ctx(), a.l, b.l, r.l, 1)); return r; }
+  // Div (field.rs:277-299): x * y^-1; the reference asserts y != 0 (:285)
+  friend FieldElement operator/(const FieldElement& a, const FieldElement& b) {
+    if (b == zero()) throw Error(ZC_ERR_NONCANONICAL, "Cannot divide by zero.");
+    FieldElement r; Gpu::instance().check(zc_fe_div_batch(Gpu::instance().ctx(), a.l, b.l, r.l, 1)); return r;
+  }
   FieldElement operator-() const { FieldElement r; Gpu::instance().check(zc_fe_neg_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }
   FieldElement square() const { FieldElement r; Gpu::instance().check(zc_fe_square_batch(Gpu::instance().ctx(), l, r.l, 1)); return r; }
   FieldElement pow(const FieldElement& e) const { FieldElement r; Gpu::instance().check(zc_fe_pow_batch(Gpu::instance().ctx(), l, e.l, r.l, 1)); return r; }   // field.rs:334-354
@@ -136,6 +141,12 @@ struct Scalar {
     return d;
   }
   std::array<int8_t, 256> compute_NAF() const { return compute_window_NAF(2); }
+  // scalar.rs:352-366: the 256 bits of the value, least significant first
+  std::array<uint8_t, 256> into_bits() const {
+    alignas(16) std::array<uint8_t, 256> b;
+    Gpu::instance().check(zc_scalar_into_bits_batch(Gpu::instance().ctx(), l, b.data(), 1));
+    return b;
+  }
   friend bool operator==(const Scalar& a, const Scalar& b) { return a.to_bytes() == b.to_bytes(); }
   friend bool operator!=(const Scalar& a, const Scalar& b) { return !(a == b); }
 };
@@ -224,6 +235,26 @@ inline RistrettoPoint msm(Gpu& g, const RistrettoPoint* points, const Scalar* sc
   g.check(zc_msm(g.ctx(), n ? points->p.limbs() : nullptr, n ? scalars->l : nullptr, n, window_bits, r.p.limbs()));
   return r;
 }
+inline void fe_div(Gpu& g, const FieldElement* a, const FieldElement* b, FieldElement* out, size_t n) { g.check(zc_fe_div_batch(g.ctx(), a->l, b->l, out->l, n)); }
+// fixed generators (bulletproofs G_i, H_i): an owning handle over zc_msm_generators.  The handle keeps its own copy of
+// everything derived from the points, so the caller's array may be dropped or reused after construction.
+class Generators {
+ public:
+  // points_dev: n points resident on the device (the reference layout); kind ZC_GEN_PREPARED or ZC_GEN_FIXED_BASE
+  Generators(Gpu& g, const uint64_t* points_dev, size_t n, int kind = ZC_GEN_PREPARED, int window_bits = 16, int rank = 0, int nranks = 1) : g_(g) {
+    g.check(zc_msm_generators_create_dev(g.ctx(), points_dev, n, kind, window_bits, rank, nranks, &h_));
+  }
+  ~Generators() { if (h_) zc_msm_generators_destroy(g_.ctx(), h_); }
+  Generators(const Generators&) = delete;
+  Generators& operator=(const Generators&) = delete;
+  // sum_i scalars_dev[i] * G_i, result on the device
+  void msm_dev(const uint64_t* scalars_dev, uint64_t* out_point_dev, int window_bits = 16) const { g_.check(zc_msm_gen_dev(g_.ctx(), h_, scalars_dev, window_bits, out_point_dev)); }
+  void msm_sharded_dev(const uint64_t* scalars_dev, uint64_t* out_point_dev, int window_bits = 16) const { g_.check(zc_msm_gen_sharded_dev(g_.ctx(), h_, scalars_dev, window_bits, out_point_dev)); }
+  zc_msm_generators* raw() const { return h_; }
+ private:
+  Gpu& g_;
+  zc_msm_generators* h_ = nullptr;
+};
 }  // namespace batch
 
 }  // namespace zerocaf

@@ -43,9 +43,10 @@ def stress(R, K, n):
     streams, ctxs = make_ranks(R)
     out = torch.zeros((R, K, 20), dtype=torch.int64, device="cuda")
     warm = torch.zeros(20, dtype=torch.int64, device="cuda")
-    for cx in ctxs:                                   # workspace allocation synchronises the device: do it before any rank spins
-        for r in range(R):
-            cx.check(cx._L.zc_msm_partial_dev(cx._h, dP.data_ptr(), dS[0].data_ptr(), n, 16, r, R, warm.data_ptr()))
+    # Workspace allocation and the first graph instantiation synchronise the device: do both (each rank's own share of the
+    # same shape) before any rank spins in an exchange.  Later calls with other scalars only update the graph in place.
+    for r, cx in enumerate(ctxs):
+        cx.check(cx._L.zc_msm_partial_dev(cx._h, dP.data_ptr(), dS[0].data_ptr(), n, 16, r, R, warm.data_ptr()))
         cx.sync()
     # scalar set per call: runs of equal sets (graph replay) and alternation (re-capture)
     pick = [(k // 3) % 3 if k % 7 else (k % 3) for k in range(K)]
@@ -59,6 +60,9 @@ def stress(R, K, n):
     bad_val = sum(1 for k in range(K) if not o.pt_eq(res[0, k], want[pick[k]]))
     # the same ranks through generator handles (prepared points): one more exchange per rank
     gens = [cx.msm_generators(dP.data_ptr(), n, zc.GEN_PREPARED) for cx in ctxs]
+    for r, (cx, g) in enumerate(zip(ctxs, gens)):
+        g.msm_partial(dS[0].data_ptr(), warm.data_ptr(), r, R, window_bits=16)
+        cx.sync()
     out2 = torch.zeros((R, 20), dtype=torch.int64, device="cuda")
     for r, g in enumerate(gens):
         g.msm_sharded(dS[1].data_ptr(), out2[r].data_ptr(), window_bits=16)
@@ -87,8 +91,8 @@ def timeout():
     dP, dS = torch.from_numpy(P.view(np.int64)).cuda(), torch.from_numpy(s.view(np.int64)).cuda()
     streams, ctxs = make_ranks(2)
     out = torch.zeros((2, 20), dtype=torch.int64, device="cuda")
-    for cx in ctxs:
-        cx.check(cx._L.zc_msm_partial_dev(cx._h, dP.data_ptr(), dS.data_ptr(), n, 16, 0, 2, out[0].data_ptr()))
+    for r, cx in enumerate(ctxs):
+        cx.check(cx._L.zc_msm_partial_dev(cx._h, dP.data_ptr(), dS.data_ptr(), n, 16, r, 2, out[r].data_ptr()))
         cx.sync()
     # only rank 0 calls the collective
     ctxs[0].check(ctxs[0]._L.zc_msm_sharded_dev(ctxs[0]._h, dP.data_ptr(), dS.data_ptr(), n, 16, out[0].data_ptr()))

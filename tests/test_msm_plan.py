@@ -1,9 +1,10 @@
-"""Host-side invariants of the MSM plan that csrc/zc_msm.cu implements (dusk_zerocaf_b200/sharding.py restates them):
+"""Host-side invariants of the MSM plan that csrc/zc_msm.cu implements (asked from the library through dusk_zerocaf_b200/sharding.py -> zc_msm_plan_query, compared with the independent model tests/msm_plan_model.py):
 the carry-free digit recoding, the short-window sub-bucket rule, and the spread rule + constant correction of the
 fixed-base (merged bucket set) path.  Pure integer checks, no GPU."""
 import numpy as np
 
 from dusk_zerocaf_b200 import sharding
+import msm_plan_model as model
 
 L = 2**249 + 14490550575682688738086195780655237219
 
@@ -20,8 +21,8 @@ def test_offset_recoding_equals_carry_recoding():
     rng = np.random.default_rng(11)
     for c in range(8, 17):
         for s in _scalars(rng):
-            d = sharding.offset_digits(s, c)
-            assert d == sharding.signed_digits(s, c), (c, s)
+            d = model.offset_digits(s, c)
+            assert d == model.signed_digits(s, c), (c, s)
             assert sum(x << (c * w) for w, x in enumerate(d)) == s
 
 
@@ -32,7 +33,7 @@ def test_short_windows_only_see_small_nonnegative_digits():
     rng = np.random.default_rng(12)
     for c in range(8, 17):
         for s in _scalars(rng, 400):
-            d = sharding.offset_digits(s, c)
+            d = model.offset_digits(s, c)
             for w, x in enumerate(d):
                 ba = 250 - c * w
                 if ba == 0:
@@ -63,13 +64,13 @@ def test_fixed_base_spread_weights_fit_and_sum_to_the_scalar():
         sms = [sharding.merged_spread_bits(c, w) for w in range(nwin)]
         assert sum(1 for x in sms if x) <= 1                     # at most one spread window per scalar width
         for s in _scalars(rng, 300):
-            d = sharding.offset_digits(s, c)
+            d = model.offset_digits(s, c)
             for i in (0, 1, 5, 2**20 - 1, 12345):
                 total, corr = 0, 0
                 for w in range(nwin):
                     sh = sharding.fixed_base_row_shift(c, w)
                     if sms[w]:
-                        wgt = sharding.spread_digit(d[w], i, sms[w])
+                        wgt = model.spread_digit(d[w], i, sms[w])
                         assert 0 <= wgt <= (1 << (c - 1)), (c, w, s, i, wgt)
                         corr += (i & ((1 << sms[w]) - 1)) << sh
                         assert sh + sms[w] == c * w and ((i & ((1 << sms[w]) - 1)) << sh) < L   # the correction scalars are canonical
@@ -86,3 +87,17 @@ def test_fixed_base_table_size():
     assert sharding.fixed_base_table_rows(16, 20, 32, 1000) == 0                        # a rank beyond the window count
     assert sharding.fixed_base_row_shift(16, 15) == 236 and sharding.merged_spread_bits(16, 15) == 4
     assert sharding.short_window_sub_bits(16, 15) == 5 and sharding.short_window_sub_bits(16, 14) == 0
+
+
+def test_library_plan_rules_equal_the_model():
+    """zc_msm_plan_query (the C side) against the model, every window size and window, several rank counts."""
+    for c in range(8, 17):
+        for w in range(model.num_windows(c)):
+            assert sharding.short_window_sub_bits(c, w) == model.short_window_sub_bits(c, w), (c, w)
+            assert sharding.merged_spread_bits(c, w) == model.merged_spread_bits(c, w), (c, w)
+            assert sharding.fixed_base_row_shift(c, w) == model.fixed_base_row_shift(c, w), (c, w)
+            for R in (1, 2, 3, 4, 8, 16, 32):
+                assert sharding.plan_query(c, w, R)[0] == model.window_owner(w, R), (c, w, R)
+    # the pairing the boustrophedon order buys at 8 ranks, 16 windows: rank r owns windows r and 15 - r
+    assert [sharding.windows_of_rank(16, r, 8) for r in range(8)] == [[r, 15 - r] for r in range(8)]
+    assert sharding.windows_of_rank(16, 0, 4) == [0, 7, 8, 15]

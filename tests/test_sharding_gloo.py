@@ -12,6 +12,7 @@ import torch.multiprocessing as mp
 
 from conftest import SEED
 from dusk_zerocaf_b200 import sharding, synth
+import msm_plan_model as model
 
 
 def test_window_plan():
@@ -24,7 +25,7 @@ def test_window_plan():
     for c in range(8, 17):
         for s in [0, 1, L - 1, 2**249 - 1, 2**(c - 1), 2**c - 1] + [int(rng.integers(0, 2**62)) << 180 for _ in range(20)]:
             s %= L
-            d = sharding.signed_digits(s, c)
+            d = model.signed_digits(s, c)
             assert sum(x << (c * w) for w, x in enumerate(d)) == s
             assert all(-(1 << (c - 1)) <= x < (1 << (c - 1)) for x in d)
 
@@ -46,7 +47,7 @@ def test_task_plan_covers_every_window_point_once():
 def _model_partial(o, P, S, c, rank, world):
     """One rank's partial point: Horner over all windows, adding only the (window, point range) tasks it owns."""
     n = P.shape[0]
-    digs = [sharding.signed_digits(sharding.limbs_to_int(S[i]), c) for i in range(n)]
+    digs = [model.signed_digits(model.limbs_to_int(S[i]), c) for i in range(n)]
     nwin = sharding.num_windows(c)
     mine = {w: (p0, p1) for w, p0, p1 in sharding.tasks_of_rank(c, rank, world, n)}
     acc, started = o.pt_identity(), False
