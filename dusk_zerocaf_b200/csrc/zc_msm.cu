@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t* __restr
 // stitch the buckets that span several segments.  Every thread does the same number of additions, whatever the digit
 // distribution (a top window with few, heavy buckets used to serialise thousands of additions in one thread).
 constexpr int SEG_MAX = 32;           // segment length is 8, 16 or 32 (chosen per call from the amount of work)
-constexpr int ACC_TPB = 128;
+// threads per accumulation block: 128 (ZC_MSM_ACC_TPB=64 selects 64-thread blocks, an experiment: a launch of 512 blocks on 592
+// slots leaves the SMs unevenly loaded, but finer blocks measured the same time -- the kernel is bound by the dependent
+// multiplications of each thread's segment, not by the busiest SM)
+constexpr int ACC_TPB_MAX = 128;
 
 // Operands are gathered into shared memory with cp.async (no register staging) one entry ahead of the addition that
 // uses them, and the addition reads each 32-byte coordinate from shared memory right before the multiplication that
@@ -288,6 +291,7 @@ constexpr int ACC_TPB = 128;
 // Stage layout: [buffer 0..1][16-byte piece 0..7][thread]; pieces 0-1 = Y+X, 2-3 = Y-X, 4-5 = Z, 6-7 = 2dT.
 constexpr int ACC_NBUF = 2;
 
+template <int ACC_TPB>
 __device__ __forceinline__ void gather_entry(uint4* __restrict__ stage_buf, const uint32_t* __restrict__ cached, uint32_t e, int tx) {
   const uint32_t* src = cached + 32 * (size_t)(e & 0x7fffffffu);
   const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage_buf + tx);
@@ -295,6 +299,7 @@ __device__ __forceinline__ void gather_entry(uint4* __restrict__ stage_buf, cons
   for (int k = 0; k < 8; k++)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(k * ACC_TPB * 16)), "l"(src + 4 * k) : "memory");
 }
+template <int ACC_TPB>
 __device__ __forceinline__ Fe lds_fe(const uint4* __restrict__ p) {      // two pieces, ACC_TPB apart
   const uint4 lo = p[0], hi = p[ACC_TPB];
   return Fe{{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
@@ -308,18 +313,18 @@ __device__ __noinline__ Fe acc_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
 
 // p + (+-q) with q staged in shared memory (q points at this thread's piece 0); add-2008-hwcd-3, a = -1
 // AFFINE: the staged operands have Z = 1 (prepared points are normalised once), so D = 2 Z1 needs no product: 7M.
-template <bool AFFINE>
+template <bool AFFINE, int ACC_TPB>
 __device__ __forceinline__ Pt pt_add_staged(const Pt& p, const uint4* __restrict__ q, bool neg) {
   typedef ModP M;
   // p and the staged operand are canonical; every linear combination below is lazy (no conditional subtraction): the
   // factors stay below 2m, 2m, 3m, 3m and each product below 9 m^2 < R m, which is all the Montgomery product needs
   const Fe zero{{0, 0, 0, 0, 0, 0, 0, 0}};
-  Fe A = acc_mul(fe_sub_lazy<1>(p.Y, p.X), lds_fe(q + (neg ? 0 : 2) * ACC_TPB));
-  Fe B = acc_mul(fe_add_lazy(p.Y, p.X), lds_fe(q + (neg ? 2 : 0) * ACC_TPB));
-  Fe t2d = lds_fe(q + 6 * ACC_TPB);
+  Fe A = acc_mul(fe_sub_lazy<1>(p.Y, p.X), lds_fe<ACC_TPB>(q + (neg ? 0 : 2) * ACC_TPB));
+  Fe B = acc_mul(fe_add_lazy(p.Y, p.X), lds_fe<ACC_TPB>(q + (neg ? 2 : 0) * ACC_TPB));
+  Fe t2d = lds_fe<ACC_TPB>(q + 6 * ACC_TPB);
   if (neg) t2d = fe_sub_lazy<1>(zero, t2d);                    // m - 2dT2 in (0, m]
   Fe C = acc_mul(p.T, t2d);
-  Fe D = AFFINE ? p.Z : acc_mul(p.Z, lds_fe(q + 4 * ACC_TPB));
+  Fe D = AFFINE ? p.Z : acc_mul(p.Z, lds_fe<ACC_TPB>(q + 4 * ACC_TPB));
   D = fe_dbl_lazy(D);                                          // < 2m
   Fe E = fe_sub_lazy<1>(B, A);                                 // < 2m
   Fe F = fe_sub_lazy<1>(D, C);                                 // < 3m
@@ -333,10 +338,11 @@ __device__ __forceinline__ Pt pt_add_staged(const Pt& p, const uint4* __restrict
   return r;
 }
 // the point a staged operand stands for, as (2X, 2Y, 2Z, 2T)
+template <int ACC_TPB>
 __device__ __forceinline__ Pt staged_to_pt(const uint4* __restrict__ q, bool neg) {
   typedef ModP M;
-  Fe ypx = lds_fe(q + (neg ? 2 : 0) * ACC_TPB), ymx = lds_fe(q + (neg ? 0 : 2) * ACC_TPB);
-  Fe z = lds_fe(q + 4 * ACC_TPB), t2d = lds_fe(q + 6 * ACC_TPB);
+  Fe ypx = lds_fe<ACC_TPB>(q + (neg ? 2 : 0) * ACC_TPB), ymx = lds_fe<ACC_TPB>(q + (neg ? 0 : 2) * ACC_TPB);
+  Fe z = lds_fe<ACC_TPB>(q + 4 * ACC_TPB), t2d = lds_fe<ACC_TPB>(q + 6 * ACC_TPB);
   if (neg) t2d = fe_neg<M>(t2d);
   Pt r;
   r.X = fe_sub<M>(ypx, ymx);
@@ -346,8 +352,8 @@ __device__ __forceinline__ Pt staged_to_pt(const uint4* __restrict__ q, bool neg
   return r;
 }
 
-template <bool AFFINE>
-__global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
+template <bool AFFINE, int ACC_TPB>
+__global__ void __launch_bounds__(ACC_TPB, 512 / ACC_TPB) msm_accum_kernel(const uint32_t* __restrict__ cached, const uint32_t* __restrict__ sorted,
                                                                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
                                                                size_t n_pad, int nseg, int seg, int nwl, int nb,
                                                                uint32_t* __restrict__ buckets, uint32_t* __restrict__ partH,
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
     }
   }
   uint32_t e_cur = idx_s[tx];
-  gather_entry(stage[0], cached, e_cur, tx);
+  gather_entry<ACC_TPB>(stage[0], cached, e_cur, tx);
   asm volatile("cp.async.commit_group;" ::: "memory");
   // bucket of the first entry: last b with offs[b] <= start  (upper_bound - 1)
   uint32_t lo = 0, hi = (uint32_t)nb;
@@ -394,14 +400,14 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
     uint32_t e_nxt = 0;
     if (k + 1 < end) {                       // gather the next operand under this addition
       e_nxt = idx_s[(k + 1 - start) * ACC_TPB + tx];
-      gather_entry(stage[buf ^ 1], cached, e_nxt, tx);
+      gather_entry<ACC_TPB>(stage[buf ^ 1], cached, e_nxt, tx);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");     // everything but the newest group: entry k has landed
     const uint4* q = stage[buf] + tx;
     const bool neg = (e_cur >> 31) != 0;
     if (k == start) {
-      acc = staged_to_pt(q, neg);
+      acc = staged_to_pt<ACC_TPB>(q, neg);
     } else if (k == bend) {
       // flush the finished run
       const bool complete = (run_start == bbeg);
@@ -409,9 +415,9 @@ __global__ void __launch_bounds__(ACC_TPB, 4) msm_accum_kernel(const uint32_t* _
       do { b++; } while (whist[b] == 0);
       bbeg = k; bend = k + whist[b];
       run_start = k;
-      acc = staged_to_pt(q, neg);
+      acc = staged_to_pt<ACC_TPB>(q, neg);
     } else {
-      acc = pt_add_staged<AFFINE>(acc, q, neg);
+      acc = pt_add_staged<AFFINE, ACC_TPB>(acc, q, neg);
     }
     e_cur = e_nxt;
   }
@@ -979,6 +985,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     // ev[10] chain done.
     // One GPU: the early groups' reductions have slack (low priority: they must not take SMs from the accumulation that
     // follows).  Sharded: a rank owns few windows and every reduction feeds the serial window chain -- all high priority.
+    // accumulation block size (see ACC_TPB_MAX): 64 threads when 128-thread blocks would not fill two waves of the 4-per-SM slots
+    static const int acc_tpb_env = getenv("ZC_MSM_ACC_TPB") ? atoi(getenv("ZC_MSM_ACC_TPB")) : 0;
+    auto acc_tpb = [&](size_t nthreads) -> int {
+      if (acc_tpb_env == 64 || acc_tpb_env == 128) return acc_tpb_env;
+      (void)nthreads;
+      return 128;                                 // measured at 8 ranks (one window of 2^20 entries per launch): 64-thread blocks change nothing (176 us either way)
+    };
     static const bool stitch_quad = !(getenv("ZC_MSM_STITCH_QUAD") && atoi(getenv("ZC_MSM_STITCH_QUAD")) == 0);
     static const int hi_prio_env = getenv("ZC_MSM_HI_PRIO") ? atoi(getenv("ZC_MSM_HI_PRIO")) : -1;
     const bool hi_prio = hi_prio_env >= 0 ? hi_prio_env != 0 : nranks > 1;
@@ -1069,7 +1082,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         // inline by the reduction's loads, the few heavier ones (buckets the short top window also feeds) one warp each.
         const int seg = fb_seg, nseg = (int)(n_pad / seg);
         const int fix_inline = 2 * (int)(fb_entries / ((size_t)nb * seg)) + FIX_INLINE;
-        msm_accum_kernel<true><<<(unsigned)((nseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
+        if (acc_tpb((size_t)nseg) == 64)
+          msm_accum_kernel<true, 64><<<(unsigned)((nseg + 63) / 64), 64, 0, st>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
+        else
+          msm_accum_kernel<true, 128><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
         nlaunch++; mark(st, 0, "msm_accum_kernel");
         msm_fixq_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(offs, hist, seg, 1, nb, fix_inline, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_fixq_kernel");
         msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_heavy_kernel");
@@ -1102,10 +1118,15 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         uint32_t *g_buckets = buckets + 32 * ((size_t)lo * nb), *g_partH = partH + 32 * ((size_t)lo * nseg_alloc), *g_partT = partT + 32 * ((size_t)lo * nseg_alloc);
         uint32_t *g_hcount = heavy_count + 64 * g, *g_hlist = heavy_list + (size_t)lo * nb;
         if (g == 0 && !use_prepared) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
-        if (use_prepared)
-          msm_accum_kernel<true><<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+        const int tpb = acc_tpb(tseg);
+        if (use_prepared && tpb == 64)
+          msm_accum_kernel<true, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+        else if (use_prepared)
+          msm_accum_kernel<true, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+        else if (tpb == 64)
+          msm_accum_kernel<false, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
         else
-          msm_accum_kernel<false><<<(unsigned)((tseg + ACC_TPB - 1) / ACC_TPB), ACC_TPB, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+          msm_accum_kernel<false, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
         nlaunch++; mark(st, 0, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
@@ -1115,10 +1136,11 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         // stage 1 runs ON the main stream, ahead of the next accumulation.  ZC_MSM_SEQ_STAGE1 = 0 / 1 forces it.
         static const int seq_env = getenv("ZC_MSM_SEQ_STAGE1") ? atoi(getenv("ZC_MSM_SEQ_STAGE1")) : -1;
         const int chain_after = (g == ngroups - 1) ? 0 : c * (tasks[lo].w - tasks[lo - 1].w);   // doublings this group's sums wait for
-        // Worth it when this group's chain would otherwise end after the LAST group's reduction + final scaling are ready:
-        // in-line stage 1 delays the later accumulations by ~50 us and brings this group's sums forward by ~100 us.
+        // In-line stage 1 delays the later accumulations by ~45 us and brings this group's sums forward by ~130 us: worth it
+        // when the chain that waits for them is longer than ~100 doublings (measured per rank at 8 ranks, 2^20 points).
         const int post_all = c * tasks[0].w;                     // doublings after the last group (the rank's lowest window)
-        const bool seq1 = (g < ngroups - 1) && (seq_env >= 0 ? seq_env != 0 : (nranks > 1 && g == 0 && chain_after - post_all > 118));
+        const bool seq1 = (g < ngroups - 1) && (seq_env >= 0 ? seq_env != 0 : (nranks > 1 && g == 0 && chain_after > 100));
+        (void)post_all;
         cudaStream_t s1 = seq1 ? st : side;
         const int s1id = seq1 ? 0 : 1;
         if (!seq1) {
