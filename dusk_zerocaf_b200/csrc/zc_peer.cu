@@ -139,10 +139,16 @@ int32_t zc_peer_mailbox_create(zc_ctx* ctx, uint8_t handle_out[64]) {
   if (!ctx || !handle_out) return ZC_ERR_NULL;
   ZC_CUDA(ctx, cudaSetDevice(ctx->device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  if (!ctx->mailbox) {
-    ZC_CUDA(ctx, cudaMalloc(&ctx->mailbox, sizeof(zc_mailbox)));
-    ZC_CUDA(ctx, cudaMemset(ctx->mailbox, 0, sizeof(zc_mailbox)));
-  }
+  // Always a FRESH, zeroed mailbox and sequence numbers from 0: (re)connecting is create -> exchange handles -> connect on
+  // every rank, and a mailbox is zeroed before its handle exists, so no rank can deliver into it too early.
+  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->peers_connected && ctx->peers_ipc)
+    for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && ctx->peers.p[r]) { cudaIpcCloseMemHandle(ctx->peers.p[r]); ctx->peers.p[r] = nullptr; }
+  ctx->peers_connected = false;
+  if (ctx->mailbox) { ZC_CUDA(ctx, cudaFree(ctx->mailbox)); ctx->mailbox = nullptr; }
+  ZC_CUDA(ctx, cudaMalloc(&ctx->mailbox, sizeof(zc_mailbox)));
+  ZC_CUDA(ctx, cudaMemset(ctx->mailbox, 0, sizeof(zc_mailbox)));
+  ctx->peer_seq = 0;
   cudaIpcMemHandle_t h;
   ZC_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->mailbox));
   memcpy(handle_out, &h, 64);
@@ -178,11 +184,6 @@ static int32_t peer_connect(zc_ctx* ctx, const uint8_t* handles, void* const* pt
     ctx->peers.p[r] = (zc_mailbox*)p;
   }
   ctx->peers_ipc = ptrs == nullptr;
-  // (re)connecting is collective: every rank restarts its sequence numbers and clears its own flags.  The host framework
-  // must put a barrier between the connects and the first exchange.
-  ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ZC_CUDA(ctx, cudaMemset(ctx->mailbox, 0, sizeof(zc_mailbox)));
-  ctx->peer_seq = 0;
   // always sized for THIS nranks (zc_ctx_set_nccl may have run earlier with fewer ranks)
   if (ctx->gather_buf) { ZC_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ZC_CUDA(ctx, cudaFree(ctx->gather_buf)); ctx->gather_buf = nullptr; }
   ZC_CUDA(ctx, cudaMalloc(&ctx->gather_buf, (size_t)(nranks + 1) * 160));
