@@ -211,6 +211,9 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: zerocaf_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NUMA placement before anything pins host memory: this rank's CPUs = the ones next to its GPU (no-op on a one-node VM)
+    from dusk_zerocaf_b200 import hostmem
+    placement = hostmem.bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -298,11 +301,13 @@ def run_b200(args):
         pass
 
     # ---- integer-pipe roofline (configs 3-5 are multiplier-bound, so report both rooflines) ------------------
-    # peak = the measured issue ceiling of plain IMAD.WIDE.U32 (tools/ubench/pipes.cu, profiles/r02_ubench_pipes.txt):
-    # 61.0 lanes/clk/SM.  It is scaled to the SM clock sampled under THIS load (the board runs into its power cap), and
-    # the carry-chained form the field arithmetic is made of (IMAD.WIDE.U32.X, pipes2-4: 19-22 /clk/SM; full products
-    # 23.6 /clk/SM in montbench) is given beside it as the practical ceiling of this code shape.
-    WIDE_PER_CLK_SM, WIDE_CHAINED_PER_CLK_SM = 61.0, 23.6
+    # peak = 32 wide multiply-adds / clk / SM: an IMAD.WIDE.U32[.X] of a carry chain occupies the fmaheavy pipe for 4 cycles per
+    # warp instruction (tools/ubench/pipes2-4 + montbench, profiles/r02_ubench_pipes.txt; cross-checked by ncu: the config-2
+    # kernel issues 196 of them per warp in 1049 cycles with sm__pipe_fmaheavy_cycles_active = 78.9 %, i.e. 4.2 pipe cycles
+    # each, profiles/r02_fe_mul_square_ncu.csv).  Scaled to the SM clock sampled under THIS load (the board sits on its 1 kW
+    # power cap).  A carry-free mad.wide with all operands in the reuse cache issues at 61 / clk / SM in pipes.cu; a
+    # carry-free product built on it (9 x 28-bit limbs) measured slower than the chained one (profiles/r02_pipes5_*.txt).
+    WIDE_PER_CLK_SM, WIDE_PLAIN_UBENCH = 32.0, 61.0
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     sm_count = 148
 
@@ -310,7 +315,7 @@ def run_b200(args):
         peak = WIDE_PER_CLK_SM * sm_count * sm_mhz * 1e6
         ach = work_per_unit * units_per_s
         return {"work_per_unit": work_per_unit, "achieved": ach, "peak": peak, "unit": "wide-mults/s (32x32+64 -> 64)", "frac": ach / peak,
-                "frac_of_chained_ceiling": ach / (WIDE_CHAINED_PER_CLK_SM * sm_count * sm_mhz * 1e6), "sm_mhz": sm_mhz, "note": note}
+                "peak_per_clk_per_sm": WIDE_PER_CLK_SM, "plain_mad_wide_ubench_per_clk_per_sm": WIDE_PLAIN_UBENCH, "sm_mhz": sm_mhz, "note": note}
 
     # mul-only and square-only rates (N / t_mul beside the fused 2N / t)
     dm = torch.empty_like(da)
@@ -321,10 +326,37 @@ def run_b200(args):
                 "ms_square": ms_sq / kk, "hbm_frac_mul": 96.0 * n / (ms_mul / kk * 1e-3) / 1e9 / peak,
                 "roofline_int_mul": roofline_int(112, n * kk / (ms_mul * 1e-3), "112 wide multiplies per Mul: 64 (8x8 words) + 32 + 16 (two folds with 2^K = -c)")}
     del dm
+    # ---- the same workload on the 32-byte wire format (to_bytes / from_bytes, field.rs:563-631): resident and end to end ----
+    pa, pb_ = torch.empty((n, 32), dtype=torch.uint8, device=dev), torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    pp, pq = torch.empty_like(pa), torch.empty_like(pa)
+    ctx.check(L.zc_fe_to_bytes_batch_dev(ctx._h, da.data_ptr(), pa.data_ptr(), n))
+    ctx.check(L.zc_fe_to_bytes_batch_dev(ctx._h, db.data_ptr(), pb_.data_ptr(), n))
+    ms_pk, _ = timed(lambda: ctx.check(L.zc_fe_mul_square_batch_packed_dev(ctx._h, pa.data_ptr(), pb_.data_ptr(), pp.data_ptr(), pq.data_ptr(), n)), args.steps, 3)
+    chk = torch.empty_like(da)
+    ctx.check(L.zc_fe_from_bytes_batch_dev(ctx._h, pp.data_ptr(), chk.data_ptr(), n))
+    ctx.sync()
+    packed_same = bool(torch.equal(chk, dp))
+    hpa, hpb = pa.cpu().pin_memory(), pb_.cpu().pin_memory()
+    hpp, hpq = torch.empty((n, 32), dtype=torch.uint8).pin_memory(), torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+    ms_pk_e2e, _ = timed(lambda: ctx.check(L.zc_fe_mul_square_batch_packed(ctx._h, hpa.data_ptr(), hpb.data_ptr(), hpp.data_ptr(), hpq.data_ptr(), n)), e2e_steps, 3)
+    traffic_pk = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic_pk = json.load(f).get("fe_mul_square_packed_kernel_bytes_per_launch")
+    except Exception:
+        pass
+    ach_pk = BYTES_PER_PAIR * n / (ms_pk / args.steps * 1e-3) / 1e9
+    packed = {"entry_point": "zc_fe_mul_square_batch_packed(_dev): 32-byte little-endian encodings in and out (the reference's to_bytes format)",
+              "value": 2.0 * n * world * args.steps / (ms_pk * 1e-3), "unit": UNIT, "ms_per_step": ms_pk / args.steps,
+              "roofline": {"bound": "hbm", "achieved": ach_pk, "peak": peak, "unit": "GB/s", "frac": ach_pk / peak, "traffic": traffic_pk},
+              "e2e": {"value": 2.0 * n * world * e2e_steps / (ms_pk_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_pk_e2e / e2e_steps,
+                      "h2d_bytes_per_step": 2 * n * 32 * world, "d2h_bytes_per_step": 2 * n * 32 * world},
+              "matches_limb_layout_results": packed_same and bool(torch.equal(hpp.to(dev), pp))}
+    del pa, pb_, pp, pq, chk, hpa, hpb, hpp, hpq
     rl_int = roofline_int(196, n / (kernel_ms * 1e-3), "196 wide multiplies per pair: Mul 112 + Square 84 (36 + 32 + 16); per GPU")
 
+    del ha, hb, hp, hs, dp, ds, da, db
     extra = {}
-    del ha, hb, hp, hs, dp, ds
     if not args.skip_extra:
         # ---- points for configs 3-5: P_i = [r_i]B from our own fixed-base kernel (Z != 1) ----------------
         def make_points(stream_id, count):
@@ -541,9 +573,11 @@ def run_b200(args):
                          "note": "algorithmic bytes = 128 B per pair (32-B canonical encodings); the kernel moves 160 B per pair in the reference's 40-B limb layout"},
             "roofline_int": rl_int,
             "mul_only": mul_only,
+            "packed_wire_format": packed,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 40 * world, "d2h_bytes_per_step": 2 * n * 40 * world,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "matches_resident_path": same},
             "gpu_launches": launches,
+            "host_placement": placement,
             "clocks": clocks,
             "cpu_baseline": cpu,
         }
