@@ -106,3 +106,41 @@ def test_cfg4_cfg5_scalar_mul_and_msm_2p20(zc, oracle, big_points):
     ctx.check(ctx._L.zc_point_fold_dev(ctx._h, parts.data_ptr(), 8, out.data_ptr()))
     ctx.sync()
     assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), msm_s)
+
+
+@pytest.mark.timeout(600)
+def test_cfg5_msm_2p20_against_the_oracle_directly(zc, oracle, big_points):
+    """the 2^20-point MSM compared with the ORACLE's naive MSM itself (fold of double_and_add over all 2^20
+    points, edwards.rs:102-120 + 465-489; ~20-30 s on the box's host threads), not with the GPU's own scalar multiplications:
+    plain call, both generator handles, and the 8-rank sharded decomposition through the in-process exchange kernel's
+    sibling path (partials + fold)."""
+    import os
+    import torch
+    from dusk_zerocaf_b200 import synth
+    n = 1 << 20
+    P = np.ascontiguousarray(big_points[:n])
+    s = synth.synth_scalar(104, 0, n)
+    want = oracle.msm_naive(P, s, threads=os.cpu_count() or THREADS)
+    assert oracle.pt_is_valid(want)
+    ctx = zc.default_context()
+    L = ctx._L
+    got = zc.batch.msm(P, s, window_bits=16)
+    assert oracle.pt_eq(got, want)
+    assert oracle.ris_compress(got) == oracle.ris_compress(want)
+    dP = torch.from_numpy(P.view(np.int64)).cuda()
+    dS = torch.from_numpy(s.view(np.int64)).cuda()
+    out = torch.zeros(20, dtype=torch.int64, device="cuda")
+    for kind in (zc.GEN_PREPARED, zc.GEN_FIXED_BASE):
+        g = ctx.msm_generators(dP.data_ptr(), n, kind, 16, 0, 1)
+        g.msm(dS.data_ptr(), out.data_ptr(), window_bits=16)
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want), kind
+        g.close()
+    parts = torch.zeros((8, 20), dtype=torch.int64, device="cuda")
+    g = ctx.msm_generators(dP.data_ptr(), n, zc.GEN_PREPARED)
+    for r in range(8):
+        g.msm_partial(dS.data_ptr(), parts[r].data_ptr(), r, 8, window_bits=16)
+    ctx.check(L.zc_point_fold_dev(ctx._h, parts.data_ptr(), 8, out.data_ptr()))
+    ctx.sync()
+    assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want)
+    g.close()
