@@ -158,15 +158,11 @@ __global__ void __launch_bounds__(256) msm_spread_scalars_kernel(uint64_t* __res
 }
 
 
-template <int C>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, const WinMap map,
-                                                         int32_t* __restrict__ digits, uint32_t* __restrict__ ranks,
-                                                         uint32_t* __restrict__ hist) {
+// The entries one scalar contributes: f(wl, key) for every window of the map, key = sign * (bucket slot + 1), 0 = no entry.
+template <int C, class F>
+__device__ __forceinline__ void msm_scalar_entries(const uint64_t* __restrict__ sp, uint32_t i, const WinMap& map, F&& f) {
   constexpr int NWIN = (256 + C - 1) / C;
   constexpr uint32_t HALF = 1u << (C - 1), MASK = (1u << C) - 1u, NB = HALF;
-  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t* sp = scalars + 5 * i;
   const uint64_t l0 = sp[0], l1 = sp[1], l2 = sp[2], l3 = sp[3], l4 = sp[4];
   // 5 x 52-bit limbs -> 64-bit words, plus H (compile-time constant), 320 bits
   uint64_t v[5];
@@ -212,14 +208,178 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restr
           key = dd < 0 ? -(int32_t)(slot + 1u) : (int32_t)(slot + 1u);
         }
       }
-      if (key != 0) {
-        const uint32_t slot = (uint32_t)(key < 0 ? -key : key) - 1u;
-        // the histogram atomic also hands out this entry's rank inside its bucket: the scatter needs no second atomic
-        ranks[(size_t)wl * n + i] = atomicAdd(&hist[(map.merged ? (size_t)0 : (size_t)wl * NB) + slot], 1u);
-      }
-      digits[(size_t)wl * n + i] = key;
+      f(wl, key);
     }
   }
+}
+
+// Sort A (ZC_MSM_SORT=atomic; the round-1 sort): one thread per scalar, a global histogram atomic per entry which also
+// hands out the entry's rank inside its bucket, then msm_scan_kernel and msm_scatter_kernel.
+template <int C>
+__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* __restrict__ scalars, size_t n, const WinMap map,
+                                                         int32_t* __restrict__ digits, uint32_t* __restrict__ ranks,
+                                                         uint32_t* __restrict__ hist) {
+  constexpr uint32_t NB = 1u << (C - 1);
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  msm_scalar_entries<C>(scalars + 5 * i, (uint32_t)i, map, [&](int wl, int32_t key) {
+    if (key != 0) {
+      const uint32_t slot = (uint32_t)(key < 0 ? -key : key) - 1u;
+      ranks[(size_t)wl * n + i] = atomicAdd(&hist[(map.merged ? (size_t)0 : (size_t)wl * NB) + slot], 1u);
+    }
+    digits[(size_t)wl * n + i] = key;
+  });
+}
+
+// Sort B (default): a two-level counting sort with no global atomics.  The 2^(c-1) buckets of a bucket set ("problem": one
+// local window, or the merged set of the fixed-base path) are cut into 2^CB coarse bins of 2^FB buckets.
+//   count   every block walks its contiguous chunk of the scalars and counts its entries per (problem, bin) in shared memory
+//   bscan   one warp per bin: exclusive scan of the per-block counts (where each block's entries start inside the bin) + bin total
+//   place   the same walk again (the scalars are L2-resident; recomputing the digits is cheaper than storing them): an entry
+//           goes to  bin start + block's offset + its rank among the block's entries of that bin (shared-memory atomic)
+//   fine    one block per bin: histogram of the 2^FB buckets in shared memory, scan, write hist[] / offs[] for the bin's
+//           buckets and the entries in bucket order
+// Entry order inside a bucket is arbitrary (as with sort A); any digit distribution is handled (a bin that takes every
+// entry is sorted by one block, slowly but correctly).
+struct SortPlan { int cb, fb; uint32_t chunk; int lo; };      // coarse / fine bits, scalars per block, first local window of the sort
+constexpr int SORT_TPB = 512;
+constexpr int FINE_TPB = 512, FINE_CAP = 9216;                 // msm_sort_fine_kernel sorts a bin of up to FINE_CAP entries in shared memory (12 B each, 108 KiB: two blocks per SM)
+// coarse bits: bins of ~2^13 entries (one msm_sort_fine block each, staged in shared memory), at most 2^8 buckets per bin
+static int sort_coarse_bits(int bits, size_t entries_per_problem, int nprob_max) {
+  int cb = 0;
+  while (cb < 9 && ((size_t)8192 << cb) < entries_per_problem) cb++;
+  if (cb < bits - 8) cb = bits - 8;
+  if (cb > bits) cb = bits;
+  while (cb > 0 && cb > bits - 8 && ((size_t)nprob_max << cb) > 4096) cb--;
+  return cb;
+}
+
+// counts[bin][block]
+template <int C>
+__global__ void __launch_bounds__(SORT_TPB) msm_sort_count_kernel(const uint64_t* __restrict__ scalars, size_t n, const WinMap map,
+                                                                  const SortPlan pl, int nbins, uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t sort_sm[];
+  for (int t = threadIdx.x; t < nbins; t += SORT_TPB) sort_sm[t] = 0;
+  __syncthreads();
+  const uint32_t beg = blockIdx.x * pl.chunk, end = (size_t)beg + pl.chunk < n ? beg + pl.chunk : (uint32_t)n;
+  for (uint32_t i = beg + threadIdx.x; i < end; i += SORT_TPB)
+    msm_scalar_entries<C>(scalars + 5 * (size_t)i, i, map, [&](int wl, int32_t key) {
+      if (key == 0) return;
+      const uint32_t slot = (uint32_t)(key < 0 ? -key : key) - 1u;
+      const uint32_t prob = map.merged ? 0u : (uint32_t)(wl - pl.lo);
+      atomicAdd(&sort_sm[(prob << pl.cb) | (slot >> pl.fb)], 1u);
+    });
+  __syncthreads();
+  for (int t = threadIdx.x; t < nbins; t += SORT_TPB) counts[(size_t)t * gridDim.x + blockIdx.x] = sort_sm[t];
+}
+
+// one warp per bin: lane l owns the blocks [l per, (l+1) per) -- all loads in flight at once, one shuffle scan
+constexpr int BSCAN_PER = 20;                                 // >= ceil(max blocks / 32): up to 640 blocks
+__global__ void __launch_bounds__(128) msm_sort_bscan_kernel(uint32_t* __restrict__ counts, int nblk, int nbins, uint32_t* __restrict__ totals) {
+  const int bin = (int)((blockIdx.x * 128 + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (bin >= nbins) return;
+  uint32_t* row = counts + (size_t)bin * nblk;
+  const int per = (nblk + 31) / 32, b0 = lane * per;
+  uint32_t x[BSCAN_PER];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < BSCAN_PER; k++) { x[k] = (k < per && b0 + k < nblk) ? row[b0 + k] : 0u; sum += x[k]; }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+  uint32_t run = inc - sum;
+#pragma unroll
+  for (int k = 0; k < BSCAN_PER; k++) if (k < per && b0 + k < nblk) { row[b0 + k] = run; run += x[k]; }
+  if (lane == 31) totals[bin] = inc;
+}
+
+// tmp[pos] = fine key << 32 | entry
+template <int C>
+__global__ void __launch_bounds__(SORT_TPB) msm_sort_place_kernel(const uint64_t* __restrict__ scalars, size_t n, size_t n_pad, const WinMap map,
+                                                                  const SortPlan pl, int nbins, const uint32_t* __restrict__ counts,
+                                                                  const uint32_t* __restrict__ totals, uint32_t* __restrict__ binstart,
+                                                                  uint64_t* __restrict__ tmp) {
+  extern __shared__ uint32_t sort_sm[];
+  uint32_t* base = sort_sm;                    // where this block's next entry of a bin goes (within the problem's array)
+  uint32_t* cnt = sort_sm + nbins;             // the bin totals
+  for (int t = threadIdx.x; t < nbins; t += SORT_TPB) cnt[t] = totals[t];
+  __syncthreads();
+  for (int t = threadIdx.x; t < nbins; t += SORT_TPB) {
+    uint32_t s = 0;
+    for (int u = t & ~((1 << pl.cb) - 1); u < t; u++) s += cnt[u];
+    if (blockIdx.x == 0) binstart[t] = s;
+    base[t] = s + counts[(size_t)t * gridDim.x + blockIdx.x];
+  }
+  __syncthreads();
+  const uint32_t beg = blockIdx.x * pl.chunk, end = (size_t)beg + pl.chunk < n ? beg + pl.chunk : (uint32_t)n;
+  for (uint32_t i = beg + threadIdx.x; i < end; i += SORT_TPB)
+    msm_scalar_entries<C>(scalars + 5 * (size_t)i, i, map, [&](int wl, int32_t key) {
+      if (key == 0) return;
+      const uint32_t slot = (uint32_t)(key < 0 ? -key : key) - 1u;
+      const uint32_t sign = key < 0 ? 0x80000000u : 0u;
+      const uint32_t prob = map.merged ? 0u : (uint32_t)(wl - pl.lo);
+      const uint32_t bin = (prob << pl.cb) | (slot >> pl.fb);
+      const size_t pos = (size_t)prob * n_pad + atomicAdd(&base[bin], 1u);     // (a per-entry rank kept by the count pass instead of this atomic measured slower: 24.6 vs 19.1 us)
+      // merged: one bucket set, the entry names the table row  wl * n + i
+      const uint32_t e = (map.merged ? (uint32_t)((size_t)wl * n + i) : (uint32_t)i) | sign;
+      tmp[pos] = ((uint64_t)(slot & ((1u << pl.fb) - 1u)) << 32) | e;
+    });
+}
+
+__global__ void __launch_bounds__(FINE_TPB, 2) msm_sort_fine_kernel(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ binstart,
+                                                                    const uint32_t* __restrict__ totals, const SortPlan pl, size_t n_pad, int nb,
+                                                                    uint32_t* __restrict__ hist, uint32_t* __restrict__ offs, uint32_t* __restrict__ sorted) {
+  extern __shared__ __align__(16) uint64_t fine_sm[];           // the bin's entries (FINE_CAP + 2), then the FINE_CAP sorted entries
+  uint32_t* fine_out = reinterpret_cast<uint32_t*>(fine_sm + FINE_CAP + 2);
+  __shared__ uint32_t h[256], cur[256], wsum[8];
+  const int bin = blockIdx.x, prob = bin >> pl.cb, bl = bin & ((1 << pl.cb) - 1), nf = 1 << pl.fb;
+  const uint32_t start = binstart[bin], cnt = totals[bin], jend = start + cnt, j0 = start & ~1u, skip = start - j0;
+  const uint64_t* src = tmp + (size_t)prob * n_pad;             // 16-byte aligned (n_pad is a multiple of 32)
+  const bool fits = jend - j0 <= (uint32_t)FINE_CAP;            // block-uniform
+  if (threadIdx.x < 256) h[threadIdx.x] = 0;
+  if (fits) {
+#pragma unroll 4
+    for (uint32_t j = j0 + 2u * threadIdx.x; j < jend; j += 2u * FINE_TPB)
+      *reinterpret_cast<ulonglong2*>(fine_sm + (j - j0)) = *reinterpret_cast<const ulonglong2*>(src + j);
+  }
+  __syncthreads();
+  if (fits) {                                    // the histogram atomic also ranks the entry inside its bucket: kept beside the key
+    for (uint32_t j = threadIdx.x; j < cnt; j += FINE_TPB) {
+      const uint64_t x = fine_sm[skip + j];
+      const uint32_t key = (uint32_t)(x >> 32);
+      fine_sm[skip + j] = (x & 0xffffffffull) | ((uint64_t)((atomicAdd(&h[key], 1u) << 8) | key) << 32);
+    }
+  }
+  else      { for (uint32_t j = start + threadIdx.x; j < jend; j += FINE_TPB) atomicAdd(&h[(uint32_t)(src[j] >> 32)], 1u); }
+  __syncthreads();
+  if (threadIdx.x < 256) {                       // exclusive scan of h[0..255] (entries >= nf are zero)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t x = h[threadIdx.x];
+    uint32_t inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) wsum[wid] = inc;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t pre = 0;
+    for (int u = 0; u < wid; u++) pre += wsum[u];
+    const uint32_t ex = pre + inc - x;
+    cur[threadIdx.x] = ex;
+    if ((int)threadIdx.x < nf) {
+      const size_t b = (size_t)prob * nb + ((size_t)bl << pl.fb) + threadIdx.x;
+      hist[b] = x;
+      offs[b] = start + ex;
+    }
+  }
+  __syncthreads();
+  uint32_t* out = sorted + (size_t)prob * n_pad + start;
+  if (fits) {
+    // bucket order is made in shared memory; the bin then leaves in one coalesced copy (scattered 4-byte stores cost a 32-byte
+    // sector each at the L2: the kernel was bound by them)
+    for (uint32_t j = threadIdx.x; j < cnt; j += FINE_TPB) { const uint64_t x = fine_sm[skip + j]; const uint32_t kr = (uint32_t)(x >> 32); fine_out[cur[kr & 255u] + (kr >> 8)] = (uint32_t)x; }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += FINE_TPB) out[j] = fine_out[j];
+  }
+  else      { for (uint32_t j = start + threadIdx.x; j < jend; j += FINE_TPB) { const uint64_t x = src[j]; out[atomicAdd(&cur[(uint32_t)(x >> 32)], 1u)] = (uint32_t)x; } }
 }
 
 // ---- exclusive scan of each window's histogram (one block of SCAN_TPB threads per local window) -----------------------
@@ -357,12 +517,12 @@ __global__ void __launch_bounds__(ACC_TPB, 512 / ACC_TPB) msm_accum_kernel(const
                                                                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
                                                                size_t n_pad, int nseg, int seg, int nwl, int nb,
                                                                uint32_t* __restrict__ buckets, uint32_t* __restrict__ partH,
-                                                               uint32_t* __restrict__ partT) {
+                                                               uint32_t* __restrict__ partT, uint32_t g_lo, uint32_t g_hi) {
   __shared__ uint32_t idx_s[SEG_MAX * ACC_TPB];
   __shared__ __align__(16) uint4 stage[ACC_NBUF][8 * ACC_TPB];
   const int tx = threadIdx.x;
-  size_t g = (size_t)blockIdx.x * ACC_TPB + tx;
-  if (g >= (size_t)nwl * nseg) return;
+  size_t g = (size_t)g_lo + (size_t)blockIdx.x * ACC_TPB + tx;      // this launch covers the segments [g_lo, g_hi) of nwl * nseg
+  if (g >= (size_t)g_hi) return;
   const size_t wl = g / nseg;
   const uint32_t s = (uint32_t)(g - wl * nseg);
   const uint32_t* woffs = offs + wl * nb;
@@ -436,12 +596,14 @@ __global__ void __launch_bounds__(ACC_TPB, 512 / ACC_TPB) msm_accum_kernel(const
 // writes them into buckets[].
 static const int FIX_INLINE = getenv("ZC_MSM_FIX_INLINE") ? atoi(getenv("ZC_MSM_FIX_INLINE")) : 6;       // per-window buckets; the merged buckets of the fixed-base path choose theirs per call
 __global__ void __launch_bounds__(256) msm_fixq_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
-                                                       int seg, int nwl, int nb, int fix_inline, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+                                                       int seg, int nwl, int nb, int fix_inline, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list,
+                                                       long long lim_lo, long long lim_hi) {
   size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= (size_t)nwl * nb) return;
   const uint32_t cnt = hist[g];
   if (cnt == 0) return;
   const uint32_t o = offs[g], e = o + cnt;
+  if ((long long)e <= lim_lo || (long long)e > lim_hi) return;
   const uint32_t s_first = o / (uint32_t)seg, s_last = (e - 1) / (uint32_t)seg;
   if (s_last - s_first + 1 > (uint32_t)fix_inline) {
     uint32_t slot = atomicAdd(heavy_count, 1u);
@@ -458,7 +620,11 @@ __device__ __noinline__ Pt pt_double_ni(Pt p) { return pt_double_fast(p); }
 struct BucketSrc {                  // where a group's buckets live (all pointers relative to the group's first window)
   const uint32_t *offs, *hist, *partH, *partT, *buckets;
   int nseg, nb, seg, fix_inline;
+  // split accumulation (one bucket set accumulated by several launches over consecutive ranges of the sorted list): this
+  // launch owns the buckets whose last entry lies in (lim_lo, lim_hi] -- complete once the launch up to lim_hi has finished
+  long long lim_lo, lim_hi;
 };
+constexpr long long LIM_ALL_LO = -1, LIM_ALL_HI = 0x7fffffffffffffffll;
 // bucket g of the group, stitched from its segment partials when it spans a few segments
 __device__ __forceinline__ Pt load_bucket(const BucketSrc& b, size_t g) {
   const int seg = b.seg;
@@ -715,8 +881,9 @@ __global__ void __launch_bounds__(128) msm_stitch_kernel(BucketSrc src, uint32_t
   const size_t g = (size_t)blockIdx.x * 128 + threadIdx.x;
   if (g >= total) return;
   const uint32_t cnt = src.hist[g];
-  if (cnt == 0) { st_pt(buckets + 32 * g, pt_identity_mont()); return; }
+  if (cnt == 0) { if ((long long)src.offs[g] > src.lim_lo && (long long)src.offs[g] <= src.lim_hi) st_pt(buckets + 32 * g, pt_identity_mont()); return; }
   const uint32_t o = src.offs[g], e = o + cnt;
+  if ((long long)e <= src.lim_lo || (long long)e > src.lim_hi) return;                   // another launch's bucket (split accumulation)
   const uint32_t s_first = o / (uint32_t)src.seg, s_last = (e - 1) / (uint32_t)src.seg;
   if (s_first == s_last || s_last - s_first + 1 > (uint32_t)src.fix_inline) return;     // already final
   st_pt(buckets + 32 * g, load_bucket(src, g));
@@ -729,9 +896,10 @@ __global__ void __launch_bounds__(128) msm_stitch_kernel(BucketSrc src, uint32_t
 __global__ void __launch_bounds__(128) msm_stitch_quad_kernel(BucketSrc src, uint32_t* __restrict__ buckets, size_t total) {
   const int q = threadIdx.x & 3, qbase = threadIdx.x & 28;
   const size_t g = (size_t)blockIdx.x * 32 + (threadIdx.x >> 2);
-  const bool valid = g < total;
+  bool valid = g < total;
   const uint32_t cnt = valid ? src.hist[g] : 0u;
   const uint32_t o = valid ? src.offs[g] : 0u, e = o + cnt;
+  valid = valid && (long long)e > src.lim_lo && (long long)e <= src.lim_hi;
   const uint32_t s_first = o / (uint32_t)src.seg, s_last = cnt ? (e - 1) / (uint32_t)src.seg : s_first;
   const size_t wl = valid ? g / src.nb : 0;
   const uint32_t* H = src.partH + 32 * (wl * src.nseg);
@@ -760,11 +928,17 @@ __global__ void __launch_bounds__(128) msm_stitch_quad_kernel(BucketSrc src, uin
 // in a row tree (16 quads per row); the quads that drop out of it first take the 32 column sums while quad 0 adds up
 // the block total.
 __global__ void __launch_bounds__(256) msm_cube1_quad_kernel(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ tot,
-                                                             uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0) {
+                                                             uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0,
+                                                             const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
+                                                             long long lim_lo, long long lim_hi) {
   __shared__ __align__(16) uint32_t sv[128 * 32];               // the block's buckets
   __shared__ __align__(16) uint32_t sw[64 * 32];                // row trees
   const int q = threadIdx.x & 3, qbase = threadIdx.x & 28, j = threadIdx.x >> 2, warp = threadIdx.x >> 5;
   const size_t blk = blockIdx.x;
+  if (offs) {                                                   // split accumulation: the block goes with the launch that completes its last bucket
+    const long long e = (long long)offs[blk * 128 + 127] + hist[blk * 128 + 127];
+    if (e <= lim_lo || e > lim_hi) return;
+  }
   {
     const uint4* src = reinterpret_cast<const uint4*>(buckets + 32 * (blk * 128));
     uint4* dst = reinterpret_cast<uint4*>(sv);
@@ -905,10 +1079,11 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     wmap.merged = use_fb ? 1 : 0;
     const size_t fb_entries = (size_t)nwl * n;
     const int fb_seg = fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8);
+    // ZC_MSM_SORT=atomic: the round-1 sort (one global histogram atomic per entry); default: the two-level counting sort
+    static const bool sort_atomic = getenv("ZC_MSM_SORT") && !strcmp(getenv("ZC_MSM_SORT"), "atomic");
     // workspace layout
     size_t o = 0;
     size_t o_cached = o; o = align_up(o + (gens ? 0 : n * 128), 256);
-    size_t o_digits = o; o = align_up(o + (size_t)nwl * n * 4, 256);
     // Segment length, per task group: 32 when the group holds >= 2^22 entries, 16 below that, 8 for <= 2^19 -- less work
     // gets shorter segments so that the accumulation still fills the GPU (one window of 2^20 points in 32-entry segments
     // is 256 CTAs of 32 serial additions each: latency-bound at 190 us).  Shorter segments mean more partials to stitch
@@ -916,13 +1091,21 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     // not always 8.  The partial-slot arrays are laid out for the shortest segment.
     const size_t n_pad = align_up(use_fb ? fb_entries : n, SEG_MAX);
     const int nseg_alloc = (int)(n_pad / (use_fb ? fb_seg : 8));
+    size_t o_digits = o;                                        // sort A: digits (4 B per entry); sort B: coarse-sorted entries (8 B)
+    o = align_up(o + ((size_t)nwl * n > (size_t)nwb * n_pad ? (size_t)nwl * n : (size_t)nwb * n_pad) * 8 + 256, 256);
     size_t o_sorted = o; o = align_up(o + (size_t)nwb * n_pad * 4 + 256, 256);
     size_t o_partH = o; o = align_up(o + (size_t)nwb * nseg_alloc * 128, 256);
     size_t o_partT = o; o = align_up(o + (size_t)nwb * nseg_alloc * 128, 256);
-    size_t o_heavy = o; o = align_up(o + 256 * MAX_GROUPS + (size_t)nwb * nb * 4, 256);
+    size_t o_heavy = o; o = align_up(o + 256 * MAX_GROUPS + (size_t)nwb * nb * 4 * (use_fb ? MAX_GROUPS : 1), 256);
     size_t o_hist = o;   o = align_up(o + (size_t)nwb * nb * 4, 256);
     size_t o_offs = o;   o = align_up(o + (size_t)nwb * nb * 4, 256);
-    size_t o_ranks = o;  o = align_up(o + (size_t)nwl * n * 4, 256);
+    size_t o_ranks = o;  o = align_up(o + (sort_atomic ? (size_t)nwl * n * 4 : 0), 256);      // sort A only: rank of each entry inside its bucket
+    const int sort_cb = sort_coarse_bits(c - 1, use_fb ? fb_entries : n, nwb), sort_fb = c - 1 - sort_cb;
+    const int sort_nblk = (int)((n + SORT_TPB - 1) / SORT_TPB) < 4 * ctx->sm_count ? (int)((n + SORT_TPB - 1) / SORT_TPB) : 4 * ctx->sm_count;
+    if (sort_nblk > 32 * BSCAN_PER) return zc_fail(ctx, ZC_ERR_STATE, "device has more SMs than the MSM sort plans for");
+    size_t o_scount = o; o = align_up(o + ((size_t)nwb << sort_cb) * sort_nblk * 4, 256);
+    size_t o_stot = o;   o = align_up(o + ((size_t)nwb << sort_cb) * 4, 256);
+    size_t o_sbin = o;   o = align_up(o + ((size_t)nwb << sort_cb) * 4, 256);
     size_t o_buckets = o; o = align_up(o + (size_t)nwb * nb * 128, 256);
     const int bits = c - 1;                                     // nb = 2^bits, bits in 7..15
     const int a1 = 2;                                           // warps per cube block = 2^a1 (bits >= 7)
@@ -955,6 +1138,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     uint32_t *heavy_list = heavy_count + 64 * MAX_GROUPS;
     uint32_t *offs = (uint32_t*)(ws + o_offs);
     uint32_t *ranks = (uint32_t*)(ws + o_ranks);
+    uint32_t *scount = (uint32_t*)(ws + o_scount), *stot = (uint32_t*)(ws + o_stot), *sbin = (uint32_t*)(ws + o_sbin);
     uint32_t *buckets = (uint32_t*)(ws + o_buckets);
     uint32_t *btot = (uint32_t*)(ws + o_tot);
     uint32_t *pm1 = (uint32_t*)(ws + o_pm1);
@@ -965,6 +1149,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     uint32_t *comp = (uint32_t*)(ws + o_comp);
     cudaStream_t st = ctx->stream;
     if (!ctx->side_stream) {
+      ZC_CUDA(ctx, cudaFuncSetAttribute(msm_sort_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FINE_CAP + 2) * 8 + FINE_CAP * 4));
       // highest priority: the side kernels are small and latency-bound; their blocks must not queue behind the
       // accumulation's grid (observed: 4x longer when they do, and the last group's tail waits for them)
       int prio_lo = 0, prio_hi = 0;
@@ -1027,7 +1212,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     };
     auto enqueue = [&]() -> int32_t {
       mark(st, 0, "start");
-      ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwb * nb * 4, st));
+      if (sort_atomic) ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwb * nb * 4, st));
       ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
       if (!use_prepared && !use_fb) {
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
@@ -1039,6 +1224,31 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       auto sort_windows = [&](cudaStream_t s_, int sid, int lo, int hi) {
         WinMap m = wmap;
         for (int w = 0; w < MAX_WINDOWS; w++) if (m.tl[w] < lo || m.tl[w] >= hi) m.tl[w] = -1;
+        if (!sort_atomic) {
+          SortPlan pl;
+          pl.cb = sort_cb; pl.fb = sort_fb; pl.chunk = (uint32_t)((n + sort_nblk - 1) / sort_nblk); pl.lo = use_fb ? 0 : lo;
+          const int nprob = use_fb ? 1 : hi - lo, nbins = nprob << sort_cb;
+          const size_t po = use_fb ? 0 : (size_t)lo;             // this sort's first bucket set
+          uint64_t *tmp = (uint64_t*)digits + po * n_pad;
+          switch (c) {
+#define ZC_SORT_CASE(C) case C: msm_sort_count_kernel<C><<<sort_nblk, SORT_TPB, nbins * 4, s_>>>(scalars, n, m, pl, nbins, scount); break;
+            ZC_SORT_CASE(8) ZC_SORT_CASE(9) ZC_SORT_CASE(10) ZC_SORT_CASE(11) ZC_SORT_CASE(12)
+            ZC_SORT_CASE(13) ZC_SORT_CASE(14) ZC_SORT_CASE(15) ZC_SORT_CASE(16)
+#undef ZC_SORT_CASE
+          }
+          nlaunch++; mark(s_, sid, "msm_sort_count_kernel");
+          msm_sort_bscan_kernel<<<(unsigned)((nbins + 3) / 4), 128, 0, s_>>>(scount, sort_nblk, nbins, stot); nlaunch++; mark(s_, sid, "msm_sort_bscan_kernel");
+          switch (c) {
+#define ZC_SORT_CASE(C) case C: msm_sort_place_kernel<C><<<sort_nblk, SORT_TPB, 2 * nbins * 4, s_>>>(scalars, n, n_pad, m, pl, nbins, scount, stot, sbin, tmp); break;
+            ZC_SORT_CASE(8) ZC_SORT_CASE(9) ZC_SORT_CASE(10) ZC_SORT_CASE(11) ZC_SORT_CASE(12)
+            ZC_SORT_CASE(13) ZC_SORT_CASE(14) ZC_SORT_CASE(15) ZC_SORT_CASE(16)
+#undef ZC_SORT_CASE
+          }
+          nlaunch++; mark(s_, sid, "msm_sort_place_kernel");
+          msm_sort_fine_kernel<<<(unsigned)nbins, FINE_TPB, (FINE_CAP + 2) * 8 + FINE_CAP * 4, s_>>>(tmp, sbin, stot, pl, n_pad, nb, hist + po * nb, offs + po * nb, sorted + po * n_pad);
+          nlaunch++; mark(s_, sid, "msm_sort_fine_kernel");
+          return;
+        }
         const unsigned grid = (unsigned)((n + 255) / 256);
         switch (c) {
 #define ZC_DIGITS_CASE(C) case C: msm_digits_kernel<C><<<grid, 256, 0, s_>>>(scalars, n, m, digits, ranks, hist); break;
@@ -1082,22 +1292,56 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         // inline by the reduction's loads, the few heavier ones (buckets the short top window also feeds) one warp each.
         const int seg = fb_seg, nseg = (int)(n_pad / seg);
         const int fix_inline = 2 * (int)(fb_entries / ((size_t)nb * seg)) + FIX_INLINE;
-        if (acc_tpb((size_t)nseg) == 64)
-          msm_accum_kernel<true, 64><<<(unsigned)((nseg + 63) / 64), 64, 0, st>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
-        else
-          msm_accum_kernel<true, 128><<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT);
-        nlaunch++; mark(st, 0, "msm_accum_kernel");
-        msm_fixq_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(offs, hist, seg, 1, nb, fix_inline, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_fixq_kernel");
-        msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, st>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, heavy_count, heavy_list); nlaunch++; mark(st, 0, "msm_heavy_kernel");
-        const BucketSrc src = {offs, hist, partH, partT, buckets, nseg, nb, seg, fix_inline};
-        if (stitch_quad) { msm_stitch_quad_kernel<<<(unsigned)((nb + 31) / 32), 128, 0, st>>>(src, buckets, (size_t)nb); nlaunch++; mark(st, 0, "msm_stitch_quad_kernel"); }
-        else { msm_stitch_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(src, buckets, (size_t)nb); nlaunch++; mark(st, 0, "msm_stitch_kernel"); }
-        msm_cube1_quad_kernel<<<(unsigned)nblk, 256, 0, st>>>(buckets, btot, pm1, pm0); nlaunch++; mark(st, 0, "msm_cube1_quad_kernel");
-        msm_cube2a_kernel<<<(unsigned)ntask, 4 * C2A_QUADS, 0, st>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(st, 0, "msm_cube2a_kernel");
-        msm_cube2b_kernel<<<4, 128, 0, st>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(st, 0, "msm_cube2b_kernel");
+        // Split accumulation (experiment, ZC_MSM_SPLIT=2..4; off by default): the sorted list is accumulated by `parts` launches
+        // over consecutive segment ranges (each on its own stream, the block scheduler drains the earlier launch first) and the
+        // buckets a range completes are stitched and taken through stage 1 of the reduction on a high-priority side stream
+        // while the next range still accumulates.  Measured at 8 ranks, 2^20 points: 0.427 ms unsplit, 0.438 / 0.474 / 0.515 ms
+        // with 2 / 3 / 4 parts -- stage 1 is throughput-bound too (it takes from the accumulation what it hides), and the
+        // last part's cube1 / cube2a / cube2b / chain are depth-bound: half the buckets do not make them shorter.
+        static const int parts_env = getenv("ZC_MSM_SPLIT") ? atoi(getenv("ZC_MSM_SPLIT")) : 0;
+        int parts = parts_env >= 1 && parts_env <= MAX_GROUPS ? parts_env : 1;
+        if (nseg < parts * 128) parts = 1;
+        cudaStream_t acc_st[MAX_GROUPS] = {st, ctx->side_stream, ctx->side_extra[0], ctx->side_extra[1]};
+        cudaStream_t tail = parts > 1 ? ctx->side_extra[2] : st;                  // high priority
+        const int tid_ = parts > 1 ? 1 : 0;
+        if (parts > 1) {
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));                          // sorted
+          for (int p = 1; p < parts; p++) ZC_CUDA(ctx, cudaStreamWaitEvent(acc_st[p], ctx->ev[0], 0));
+        }
+        const uint32_t per = (uint32_t)(((nseg + parts - 1) / parts + 127) / 128 * 128);   // segments per part, whole blocks
+        for (int p = 0; p < parts; p++) {
+          const uint32_t g_lo = (uint32_t)p * per, g_hi = (p == parts - 1 || g_lo + per > (uint32_t)nseg) ? (uint32_t)nseg : g_lo + per;
+          if (g_lo < g_hi) {
+            if (acc_tpb((size_t)nseg) == 64)
+              msm_accum_kernel<true, 64><<<(unsigned)((g_hi - g_lo + 63) / 64), 64, 0, acc_st[p]>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT, g_lo, g_hi);
+            else
+              msm_accum_kernel<true, 128><<<(unsigned)((g_hi - g_lo + 127) / 128), 128, 0, acc_st[p]>>>((const uint32_t*)gens->table, sorted, offs, hist, n_pad, nseg, seg, 1, nb, buckets, partH, partT, g_lo, g_hi);
+            nlaunch++; mark(acc_st[p], p == 0 ? 0 : 3, "msm_accum_kernel");
+          }
+          if (parts > 1) {
+            ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + p], acc_st[p]));
+            ZC_CUDA(ctx, cudaStreamWaitEvent(tail, ctx->ev[2 + p], 0));
+          }
+          // entries below g_hi * seg are accumulated: the buckets that end there are complete
+          const long long lim_lo = p == 0 ? LIM_ALL_LO : (long long)g_lo * seg;
+          const long long lim_hi = p == parts - 1 ? LIM_ALL_HI : (long long)g_hi * seg;
+          uint32_t *hc = heavy_count + 64 * p, *hl = heavy_list + (size_t)p * nb;
+          msm_fixq_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, tail>>>(offs, hist, seg, 1, nb, fix_inline, hc, hl, lim_lo, lim_hi); nlaunch++; mark(tail, tid_, "msm_fixq_kernel");
+          msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, tail>>>(offs, hist, nseg, seg, nb, partH, partT, buckets, hc, hl); nlaunch++; mark(tail, tid_, "msm_heavy_kernel");
+          const BucketSrc src = {offs, hist, partH, partT, buckets, nseg, nb, seg, fix_inline, lim_lo, lim_hi};
+          if (stitch_quad) { msm_stitch_quad_kernel<<<(unsigned)((nb + 31) / 32), 128, 0, tail>>>(src, buckets, (size_t)nb); nlaunch++; mark(tail, tid_, "msm_stitch_quad_kernel"); }
+          else { msm_stitch_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, tail>>>(src, buckets, (size_t)nb); nlaunch++; mark(tail, tid_, "msm_stitch_kernel"); }
+          msm_cube1_quad_kernel<<<(unsigned)nblk, 256, 0, tail>>>(buckets, btot, pm1, pm0, parts > 1 ? offs : nullptr, hist, lim_lo, lim_hi); nlaunch++; mark(tail, tid_, "msm_cube1_quad_kernel");
+        }
+        msm_cube2a_kernel<<<(unsigned)ntask, 4 * C2A_QUADS, 0, tail>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(tail, tid_, "msm_cube2a_kernel");
+        msm_cube2b_kernel<<<4, 128, 0, tail>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(tail, tid_, "msm_cube2b_kernel");
         ChainGaps gaps;
         for (int i = 0; i < MAX_WINDOWS; i++) gaps.pre[i] = 0;
-        msm_chain_kernel<<<1, 32, 0, st>>>(comp, 1, 1, a1, a2, 0, gaps, 0, acc, partial, (const uint64_t*)gens->corr); nlaunch++; mark(st, 0, "msm_chain_kernel");
+        msm_chain_kernel<<<1, 32, 0, tail>>>(comp, 1, 1, a1, a2, 0, gaps, 0, acc, partial, (const uint64_t*)gens->corr); nlaunch++; mark(tail, tid_, "msm_chain_kernel");
+        if (parts > 1) {
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[10], tail));
+          ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[10], 0));
+        }
         ZC_CUDA(ctx, cudaGetLastError());
         return ZC_OK;
       }
@@ -1120,13 +1364,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         if (g == 0 && !use_prepared) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
         const int tpb = acc_tpb(tseg);
         if (use_prepared && tpb == 64)
-          msm_accum_kernel<true, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+          msm_accum_kernel<true, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
         else if (use_prepared)
-          msm_accum_kernel<true, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+          msm_accum_kernel<true, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
         else if (tpb == 64)
-          msm_accum_kernel<false, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+          msm_accum_kernel<false, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
         else
-          msm_accum_kernel<false, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT);
+          msm_accum_kernel<false, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
         nlaunch++; mark(st, 0, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
@@ -1147,9 +1391,9 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
           ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
           ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
         }
-        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s1>>>(g_offs, g_hist, seg, gsz, nb, FIX_INLINE, g_hcount, g_hlist); nlaunch++; mark(s1, s1id, "msm_fixq_kernel");
+        msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s1>>>(g_offs, g_hist, seg, gsz, nb, FIX_INLINE, g_hcount, g_hlist, LIM_ALL_LO, LIM_ALL_HI); nlaunch++; mark(s1, s1id, "msm_fixq_kernel");
         msm_heavy_kernel<<<2 * ctx->sm_count, 128, 0, s1>>>(g_offs, g_hist, nseg, seg, nb, g_partH, g_partT, g_buckets, g_hcount, g_hlist); nlaunch++; mark(s1, s1id, "msm_heavy_kernel");
-        const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb, seg, FIX_INLINE};
+        const BucketSrc src = {g_offs, g_hist, g_partH, g_partT, g_buckets, nseg, nb, seg, FIX_INLINE, LIM_ALL_LO, LIM_ALL_HI};
         // A short (top) window spreads each digit over 2^sub sub-buckets.  sub == A0: the sub-bucket index is exactly the
         // lane digit of the cube, which then simply carries weight 0 (drop).  Otherwise sum the sub-buckets back first.
         uint32_t raw_mask = 0; int drop_wl = -1;
@@ -1173,7 +1417,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
         if (quad_stage1) {
           msm_cube1_quad_kernel<<<(unsigned)((size_t)gsz * nblk), 256, 0, s1>>>(g_buckets, btot + 32 * ((size_t)lo * nblk),
-              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(s1, s1id, "msm_cube1_quad_kernel");
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), nullptr, nullptr, LIM_ALL_LO, LIM_ALL_HI); nlaunch++; mark(s1, s1id, "msm_cube1_quad_kernel");
         } else {
           msm_cube1_kernel<<<(unsigned)((size_t)gsz * nblk), 32 * nw1, cube_smem, s1>>>(src, raw_mask, a1, btot + 32 * ((size_t)lo * nblk),
               pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(s1, s1id, "msm_cube1_kernel");
