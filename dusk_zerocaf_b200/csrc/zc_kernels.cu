@@ -90,10 +90,13 @@ __global__ void __launch_bounds__(TPB) fe_mul_square_packed_kernel(const uint8_t
 // ---- K2: point add / sub / double / neg on the ABI layout, limb-exact (edwards.rs:440-592) ----------------
 enum PtOp { PT_ADD = 0, PT_SUB = 1, PT_DOUBLE = 2, PT_NEG = 3 };
 
-template <int OP>
-__global__ void __launch_bounds__(TPB) pt_op_kernel(const uint64_t* __restrict__ p, const uint64_t* __restrict__ q,
-                                                    uint64_t* __restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+// Block shape: BT threads, at least MINB resident blocks per SM (the register cap that goes with it).  The default is
+// chosen by measurement at 2^22 additions (ZC_PT_VARIANT = 0: 256 x 2, 111 registers, 0.840 ms; 1: 128 x 4, 0.835 ms;
+// 2 (default): 128 x 5, 96 registers, 0.823 ms; 3: 128 x 6, 80 registers, 0.866 ms).
+template <int OP, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB) pt_op_kernel(const uint64_t* __restrict__ p, const uint64_t* __restrict__ q,
+                                                         uint64_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * BT + threadIdx.x;
   if (i >= n) return;
   Pt a = pt_load52(p + 20 * i);
   Pt r;
@@ -221,7 +224,10 @@ constexpr int SM_FAST_TPB = 128;
 // One out-of-line multiplier keeps the window loop (a doubling and an addition, 16 products) at a few KB of code instead
 // of ~60 KB of inlined carry chains: with 16 warps per SM spread over the loop, instruction fetch was a visible stall.
 __device__ __noinline__ Fe smf_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
-__device__ __forceinline__ Pt smf_double(const Pt& p) {           // pt_double_fast (dbl-2008-hwcd, a = -1)
+// need_t == false: the caller's next operation is a doubling, which reads X, Y, Z only -- T3 = E H is skipped (the T of the
+// returned point is then stale).  Three of the four doublings of a window and every window addition but the last run that
+// way: 36 instead of 40 products per window.  need_t is uniform over the grid (a loop counter), never a divergent branch.
+__device__ __forceinline__ Pt smf_double(const Pt& p, bool need_t) {           // pt_double_fast (dbl-2008-hwcd, a = -1)
   typedef ModP M;
   Fe A = smf_mul(p.X, p.X), B = smf_mul(p.Y, p.Y), Z2 = smf_mul(p.Z, p.Z);
   Fe C = fe_add<M>(Z2, Z2);
@@ -231,9 +237,11 @@ __device__ __forceinline__ Pt smf_double(const Pt& p) {           // pt_double_f
   Fe G = fe_add<M>(D, B);
   Fe F = fe_sub<M>(G, C);
   Fe H = fe_sub<M>(D, B);
-  return Pt{smf_mul(E, F), smf_mul(G, H), smf_mul(F, G), smf_mul(E, H)};
+  Pt r{smf_mul(E, F), smf_mul(G, H), smf_mul(F, G), p.T};
+  if (need_t) r.T = smf_mul(E, H);
+  return r;
 }
-__device__ __forceinline__ Pt smf_add(const Pt& p, const PtCached& q) {   // pt_add_cached (add-2008-hwcd-3)
+__device__ __forceinline__ Pt smf_add(const Pt& p, const PtCached& q, bool need_t) {   // pt_add_cached (add-2008-hwcd-3)
   typedef ModP M;
   Fe A = smf_mul(fe_sub<M>(p.Y, p.X), q.YmX);
   Fe B = smf_mul(fe_add<M>(p.Y, p.X), q.YpX);
@@ -241,7 +249,9 @@ __device__ __forceinline__ Pt smf_add(const Pt& p, const PtCached& q) {   // pt_
   Fe D = smf_mul(p.Z, q.Z);
   D = fe_add<M>(D, D);
   Fe E = fe_sub<M>(B, A), F = fe_sub<M>(D, C), G = fe_add<M>(D, C), H = fe_add<M>(B, A);
-  return Pt{smf_mul(E, F), smf_mul(G, H), smf_mul(F, G), smf_mul(E, H)};
+  Pt r{smf_mul(E, F), smf_mul(G, H), smf_mul(F, G), p.T};
+  if (need_t) r.T = smf_mul(E, H);
+  return r;
 }
 __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const uint64_t* __restrict__ points,
                                                                          const uint64_t* __restrict__ scalars,
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const u
       Pt acc = P;
 #pragma unroll 1
       for (int e = 1; e < 8; e++) {
-        acc = smf_add(acc, c1);
+        acc = smf_add(acc, c1, true);
         store_entry(e, pt_to_cached(acc));
       }
     }
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const u
     for (int j = 63; j >= 0; j--) {
       if (j != 63) {
 #pragma unroll 1
-        for (int r = 0; r < 4; r++) Q = smf_double(Q);
+        for (int r = 0; r < 4; r++) Q = smf_double(Q, r == 3);       // only the doubling in front of the addition needs T
       }
       uint32_t nib = 0;
 #pragma unroll
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const u
       if (__any_sync(0xffffffffu, mag != 0)) {
         PtCached c = load_entry(mag ? mag - 1 : 0);
         if (d < 0) c = pt_cached_neg(c);
-        Pt r = smf_add(Q, c);
+        Pt r = smf_add(Q, c, j == 0);                                  // doublings follow unless this is the last window
         if (mag != 0) Q = r;
       }
     }
@@ -408,7 +418,11 @@ int32_t launch_pt(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* o
     if ((rc = validation_enqueue<ModP>(ctx, p, 4 * n, 4 * ctx->vbase))) return rc;
     if (q && (rc = validation_enqueue<ModP>(ctx, q, 4 * n, 4 * ctx->vbase))) return rc;
   }
-  pt_op_kernel<OP><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(p, q, out, n);
+  static const int variant = getenv("ZC_PT_VARIANT") ? atoi(getenv("ZC_PT_VARIANT")) : 2;
+  if (variant == 1) pt_op_kernel<OP, 128, 4><<<grid_for(n, 128), 128, 0, ctx->stream>>>(p, q, out, n);
+  else if (variant == 3) pt_op_kernel<OP, 128, 6><<<grid_for(n, 128), 128, 0, ctx->stream>>>(p, q, out, n);
+  else if (variant != 0) pt_op_kernel<OP, 128, 5><<<grid_for(n, 128), 128, 0, ctx->stream>>>(p, q, out, n);
+  else pt_op_kernel<OP, TPB, 2><<<grid_for(n, TPB), TPB, 0, ctx->stream>>>(p, q, out, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
   return ZC_OK;

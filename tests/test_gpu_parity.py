@@ -225,6 +225,16 @@ def test_basepoint_mul_fixed_base(zc, oracle, kats):
     # agrees with the variable-base kernels on a larger batch
     s2 = oracle.synth_scalar(SEED, 77, 0, 5000)
     assert zc.batch.ristretto_eq(zc.batch.basepoint_mul(s2), zc.batch.point_scalar_mul(np.tile(B, (5000, 1)), s2, mode=1)).all()
+    # more scalars than the persistent grid has threads (4 CTAs x 148 SMs x 128): every CTA loops, the last pass is ragged
+    n3 = 4 * 148 * 128 * 2 + 12345
+    s3 = oracle.synth_scalar(SEED, 78, 0, n3)
+    got3 = zc.batch.basepoint_mul(s3)
+    idx = np.unique(np.concatenate([np.arange(0, 40), np.arange(75776 - 20, 75776 + 20), np.arange(2 * 75776 - 20, 2 * 75776 + 20),
+                                    np.arange(n3 - 40, n3), np.random.default_rng(5).integers(0, n3, 64)]))
+    want3 = oracle.pt_scalar_mul_batch(np.tile(B, (idx.size, 1)), s3[idx], threads=8)
+    for k, i in enumerate(idx):
+        assert oracle.pt_eq(got3[i], want3[k]), int(i)
+    assert zc.batch.ristretto_eq(got3, zc.batch.point_scalar_mul(np.tile(B, (n3, 1)), s3, mode=1)).all()
 
 
 def test_ristretto_vectors_via_scalar_mul(zc, oracle, kats):
