@@ -35,13 +35,14 @@ __device__ __forceinline__ Fe POS_RANGE()         { return Fe{{0x2e7ae9f6u, 0x2c
 
 // Out of line: the exponent loops call these ~315 times; one copy keeps the kernels small.
 __device__ __noinline__ Fe mul_ni(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
+__device__ __noinline__ Fe sqr_ni(Fe a) { return mont_sqr<ModP>(a); }      // 36 + 32 wide multiplies instead of 64 + 32
 
 // a^e for a Montgomery-form a and a constant exponent whose top set bit is bit nbits-1
 __device__ __forceinline__ Fe fe_pow_const(const Fe& a, const uint32_t* __restrict__ e, int nbits) {
   Fe r = a;
 #pragma unroll 1
   for (int bit = nbits - 2; bit >= 0; bit--) {
-    r = mul_ni(r, r);
+    r = sqr_ni(r);
     if ((e[bit >> 5] >> (bit & 31)) & 1u) r = mul_ni(r, a);
   }
   return r;
@@ -72,11 +73,11 @@ __device__ __forceinline__ bool mont_is_positive(const Fe& xm) { return fe_is_po
 __device__ __forceinline__ Fe mont_inv_sqrt(const Fe& v, bool& was_square) {
   typedef ModP M;
   const Fe one = Consts<M>::R1(), i = SQRT_M1_MONT();
-  Fe v2 = mul_ni(v, v);
+  Fe v2 = sqr_ni(v);
   Fe v3 = mul_ni(v2, v);
-  Fe v7 = mul_ni(mul_ni(v3, v3), v);
+  Fe v7 = mul_ni(sqr_ni(v3), v);
   Fe r = mul_ni(v3, fe_pow_const(v7, E_SQRT, 250));
-  Fe check = mul_ni(v, mul_ni(r, r));
+  Fe check = mul_ni(v, sqr_ni(r));
   // check is one of 1, -1 (r <- i r), -i (r <- i r, non-square), i (non-square); 0 when v = 0 (r = 0 already)
   const bool minus_one = fe_eq(check, MINUS_ONE_MONT());
   was_square = minus_one || fe_eq(check, one);
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(TPB) ristretto_compress_kernel(const uint64_t*
   Fe u1 = mul_ni(fe_add<M>(P.Z, P.Y), fe_sub<M>(P.Z, P.Y));
   Fe u2 = mul_ni(P.X, P.Y);
   bool sq;
-  Fe I = mont_inv_sqrt(mul_ni(u1, mul_ni(u2, u2)), sq);
+  Fe I = mont_inv_sqrt(mul_ni(u1, sqr_ni(u2)), sq);
   Fe D1 = mul_ni(u1, I);
   Fe D2 = mul_ni(u2, I);
   Fe Zinv = mul_ni(mul_ni(D1, D2), P.T);
@@ -155,11 +156,11 @@ __global__ void __launch_bounds__(TPB) ristretto_decompress_kernel(const uint8_t
   if (!good) sn = Fe{{0, 0, 0, 0, 0, 0, 0, 0}};            // keep the arithmetic below on canonical input
   const Fe one = Consts<M>::R1();
   Fe s = to_mont<M>(sn);
-  Fe ss = mul_ni(s, s);
+  Fe ss = sqr_ni(s);
   Fe u1 = fe_sub<M>(one, ss);                              // 1 + a s^2, a = -1
   Fe u2 = fe_add<M>(one, ss);
-  Fe u2_sq = mul_ni(u2, u2);
-  Fe v = fe_sub<M>(fe_neg<M>(mul_ni(D_MONT(), mul_ni(u1, u1))), u2_sq);
+  Fe u2_sq = sqr_ni(u2);
+  Fe v = fe_sub<M>(fe_neg<M>(mul_ni(D_MONT(), sqr_ni(u1))), u2_sq);
   bool sq;
   Fe I = mont_inv_sqrt(mul_ni(v, u2_sq), sq);
   good = good && sq;
@@ -189,9 +190,9 @@ __global__ void __launch_bounds__(TPB) pt_is_valid_kernel(const uint64_t* __rest
   size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (idx >= n) return;
   Fe X = to_mont<M>(fe_load52(p + 20 * idx)), Y = to_mont<M>(fe_load52(p + 20 * idx + 5)), Z = to_mont<M>(fe_load52(p + 20 * idx + 10));
-  Fe xx = mul_ni(X, X), yy = mul_ni(Y, Y), zz = mul_ni(Z, Z);
+  Fe xx = sqr_ni(X), yy = sqr_ni(Y), zz = sqr_ni(Z);
   Fe left = mul_ni(fe_sub<M>(yy, xx), zz);
-  Fe right = fe_add<M>(mul_ni(zz, zz), mul_ni(mul_ni(D_MONT(), xx), yy));
+  Fe right = fe_add<M>(sqr_ni(zz), mul_ni(mul_ni(D_MONT(), xx), yy));
   ok[idx] = fe_eq(left, right) ? 1 : 0;
 }
 
@@ -204,11 +205,11 @@ __device__ __forceinline__ Fe SQRT_AD_MINUS_ONE_MONT() { return Fe{{0x9e882cc7u,
 __device__ __forceinline__ Fe mont_sqrt_ratio_i(const Fe& u, const Fe& v, bool& was_square) {
   typedef ModP M;
   const Fe i = SQRT_M1_MONT();
-  Fe v2 = mul_ni(v, v);
+  Fe v2 = sqr_ni(v);
   Fe v3 = mul_ni(v2, v);
-  Fe v7 = mul_ni(mul_ni(v3, v3), v);
+  Fe v7 = mul_ni(sqr_ni(v3), v);
   Fe r = mul_ni(mul_ni(u, v3), fe_pow_const(mul_ni(u, v7), E_SQRT, 250));
-  Fe check = mul_ni(v, mul_ni(r, r));
+  Fe check = mul_ni(v, sqr_ni(r));
   const Fe neg_u = fe_neg<M>(u);
   const Fe neg_ui = mul_ni(neg_u, i);
   const bool correct = fe_eq(check, u), flipped = fe_eq(check, neg_u), flipped_i = fe_eq(check, neg_ui);
@@ -237,7 +238,7 @@ __device__ __forceinline__ Pt elligator_mont(const Fe& r0) {
   typedef ModP M;
   const Fe one = Consts<M>::R1(), d = D_MONT();
   Fe c = MINUS_ONE_MONT();
-  Fe r = mul_ni(SQRT_M1_MONT(), mul_ni(r0, r0));
+  Fe r = mul_ni(SQRT_M1_MONT(), sqr_ni(r0));
   Fe Ns = mul_ni(fe_add<M>(r, one), ONE_MINUS_D_SQ_MONT());
   Fe D = mul_ni(fe_sub<M>(c, mul_ni(d, r)), fe_add<M>(r, d));
   bool sq;
@@ -246,7 +247,7 @@ __device__ __forceinline__ Pt elligator_mont(const Fe& r0) {
   if (mont_is_positive(s_prim)) s_prim = fe_neg<M>(s_prim);       // s' = -|s r0|
   if (!sq) { s = s_prim; c = r; }
   Fe Nt = fe_sub<M>(mul_ni(mul_ni(c, fe_sub<M>(r, one)), D_MINUS_ONE_SQ_MONT()), D);
-  Fe ss = mul_ni(s, s);
+  Fe ss = sqr_ni(s);
   Fe W0 = mul_ni(fe_add<M>(s, s), D);
   Fe W1 = mul_ni(Nt, SQRT_AD_MINUS_ONE_MONT());
   Fe W2 = fe_sub<M>(one, ss);

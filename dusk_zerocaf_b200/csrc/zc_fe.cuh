@@ -245,8 +245,206 @@ __device__ __forceinline__ Fe mont_mul(const Fe& a, const Fe& b) {
   reduce_once<M>(r);
   return r;
 }
+// ---- Montgomery squaring: a^2 / R mod m with 36 + 32 wide multiplies instead of 64 + 32 --------------------------------
+//   a^2 = sum_i a_i 2^(32i) * ( a_i 2^(32i) + 2 sum_{j>i} a_j 2^(32j) )
+// so row i of the CIOS loop multiplies by a_i the vector  u = (0, .., 0, a_i, a_{i+1} << 1, (2a)_{i+2}, .., (2a)_7)  -- the
+// doubled high part of a, word by word (the bit a_i hands up to word i+1 of 2a belongs to the excluded low part, hence the
+// plain shift at position i+1).  The rows below are mont_row_next with the multiplies of the i leading zero words removed:
+// in the odd-aligned chain a zero word still moves its pair two words down and passes the carry on (addc pairs), in the
+// even-aligned chain it costs nothing.  Same window bounds as a product with a multiplicand < 2^256 (2a < 2^256 for
+// a < 2^255); result (a^2 + Q m) / R < a^2 / R + m, i.e. < 2m for a < 2m.
+// (A separate full square -- sqr_wide_8 -- followed by eight reduction-only rows was measured first: bit-exact, 11 % faster
+// for a lone warp but SLOWER at full occupancy, 521 against 468 cycles per warp-squaring: its ~180 carry-ripple additions
+// run at 2 cycles each on the integer ALU pipe, which then binds instead of the multiplier pipe.  tools/ubench/sqrbench.cu)
+// ---- generated by tools/gen_sqr_rows.py: rows 1..7 of the interleaved squaring (do not edit by hand) ----
+__device__ __forceinline__ void sqr_row_1(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& u, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"
+      "madc.lo.cc.u32  %8, %16, %23, %10;\n\t"
+      "madc.hi.cc.u32  %9, %16, %23, %11;\n\t"
+      "madc.lo.cc.u32  %10, %18, %23, %12;\n\t"
+      "madc.hi.cc.u32  %11, %18, %23, %13;\n\t"
+      "madc.lo.cc.u32  %12, %20, %23, %14;\n\t"
+      "madc.hi.cc.u32  %13, %20, %23, %15;\n\t"
+      "madc.lo.cc.u32  %14, %22, %23, 0;\n\t"
+      "madc.hi.u32  %15, %22, %23, 0;\n\t"
+      "mad.lo.cc.u32   %2, %17, %23, %2;\n\t"
+      "madc.hi.cc.u32  %3, %17, %23, %3;\n\t"
+      "madc.lo.cc.u32  %4, %19, %23, %4;\n\t"
+      "madc.hi.cc.u32  %5, %19, %23, %5;\n\t"
+      "madc.lo.cc.u32  %6, %21, %23, %6;\n\t"
+      "madc.hi.cc.u32  %7, %21, %23, %7;\n\t"
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(u.w[1]), "r"(u.w[2]), "r"(u.w[3]), "r"(u.w[4]), "r"(u.w[5]), "r"(u.w[6]), "r"(u.w[7]), "r"(bi));
+}
+
+__device__ __forceinline__ void sqr_row_2(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& u, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"
+      "addc.cc.u32     %8, %10, 0;\n\t"
+      "addc.cc.u32     %9, %11, 0;\n\t"
+      "madc.lo.cc.u32  %10, %17, %22, %12;\n\t"
+      "madc.hi.cc.u32  %11, %17, %22, %13;\n\t"
+      "madc.lo.cc.u32  %12, %19, %22, %14;\n\t"
+      "madc.hi.cc.u32  %13, %19, %22, %15;\n\t"
+      "madc.lo.cc.u32  %14, %21, %22, 0;\n\t"
+      "madc.hi.u32  %15, %21, %22, 0;\n\t"
+      "mad.lo.cc.u32   %2, %16, %22, %2;\n\t"
+      "madc.hi.cc.u32  %3, %16, %22, %3;\n\t"
+      "madc.lo.cc.u32  %4, %18, %22, %4;\n\t"
+      "madc.hi.cc.u32  %5, %18, %22, %5;\n\t"
+      "madc.lo.cc.u32  %6, %20, %22, %6;\n\t"
+      "madc.hi.cc.u32  %7, %20, %22, %7;\n\t"
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(u.w[2]), "r"(u.w[3]), "r"(u.w[4]), "r"(u.w[5]), "r"(u.w[6]), "r"(u.w[7]), "r"(bi));
+}
+
+__device__ __forceinline__ void sqr_row_3(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& u, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"
+      "addc.cc.u32     %8, %10, 0;\n\t"
+      "addc.cc.u32     %9, %11, 0;\n\t"
+      "madc.lo.cc.u32  %10, %16, %21, %12;\n\t"
+      "madc.hi.cc.u32  %11, %16, %21, %13;\n\t"
+      "madc.lo.cc.u32  %12, %18, %21, %14;\n\t"
+      "madc.hi.cc.u32  %13, %18, %21, %15;\n\t"
+      "madc.lo.cc.u32  %14, %20, %21, 0;\n\t"
+      "madc.hi.u32  %15, %20, %21, 0;\n\t"
+      "mad.lo.cc.u32   %4, %17, %21, %4;\n\t"
+      "madc.hi.cc.u32  %5, %17, %21, %5;\n\t"
+      "madc.lo.cc.u32  %6, %19, %21, %6;\n\t"
+      "madc.hi.cc.u32  %7, %19, %21, %7;\n\t"
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(u.w[3]), "r"(u.w[4]), "r"(u.w[5]), "r"(u.w[6]), "r"(u.w[7]), "r"(bi));
+}
+
+__device__ __forceinline__ void sqr_row_4(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& u, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"
+      "addc.cc.u32     %8, %10, 0;\n\t"
+      "addc.cc.u32     %9, %11, 0;\n\t"
+      "addc.cc.u32     %10, %12, 0;\n\t"
+      "addc.cc.u32     %11, %13, 0;\n\t"
+      "madc.lo.cc.u32  %12, %17, %20, %14;\n\t"
+      "madc.hi.cc.u32  %13, %17, %20, %15;\n\t"
+      "madc.lo.cc.u32  %14, %19, %20, 0;\n\t"
+      "madc.hi.u32  %15, %19, %20, 0;\n\t"
+      "mad.lo.cc.u32   %4, %16, %20, %4;\n\t"
+      "madc.hi.cc.u32  %5, %16, %20, %5;\n\t"
+      "madc.lo.cc.u32  %6, %18, %20, %6;\n\t"
+      "madc.hi.cc.u32  %7, %18, %20, %7;\n\t"
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(u.w[4]), "r"(u.w[5]), "r"(u.w[6]), "r"(u.w[7]), "r"(bi));
+}
+
+__device__ __forceinline__ void sqr_row_5(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& u, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"
+      "addc.cc.u32     %8, %10, 0;\n\t"
+      "addc.cc.u32     %9, %11, 0;\n\t"
+      "addc.cc.u32     %10, %12, 0;\n\t"
+      "addc.cc.u32     %11, %13, 0;\n\t"
+      "madc.lo.cc.u32  %12, %16, %19, %14;\n\t"
+      "madc.hi.cc.u32  %13, %16, %19, %15;\n\t"
+      "madc.lo.cc.u32  %14, %18, %19, 0;\n\t"
+      "madc.hi.u32  %15, %18, %19, 0;\n\t"
+      "mad.lo.cc.u32   %6, %17, %19, %6;\n\t"
+      "madc.hi.cc.u32  %7, %17, %19, %7;\n\t"
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(u.w[5]), "r"(u.w[6]), "r"(u.w[7]), "r"(bi));
+}
+
+__device__ __forceinline__ void sqr_row_6(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& u, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"
+      "addc.cc.u32     %8, %10, 0;\n\t"
+      "addc.cc.u32     %9, %11, 0;\n\t"
+      "addc.cc.u32     %10, %12, 0;\n\t"
+      "addc.cc.u32     %11, %13, 0;\n\t"
+      "addc.cc.u32     %12, %14, 0;\n\t"
+      "addc.cc.u32     %13, %15, 0;\n\t"
+      "madc.lo.cc.u32  %14, %17, %18, 0;\n\t"
+      "madc.hi.u32  %15, %17, %18, 0;\n\t"
+      "mad.lo.cc.u32   %6, %16, %18, %6;\n\t"
+      "madc.hi.cc.u32  %7, %16, %18, %7;\n\t"
+      "addc.u32        %15, %15, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(u.w[6]), "r"(u.w[7]), "r"(bi));
+}
+
+__device__ __forceinline__ void sqr_row_7(uint32_t (&ev)[8], uint32_t (&od)[8], const Fe& u, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32      %0, %0, %9;\n\t"
+      "addc.cc.u32     %8, %10, 0;\n\t"
+      "addc.cc.u32     %9, %11, 0;\n\t"
+      "addc.cc.u32     %10, %12, 0;\n\t"
+      "addc.cc.u32     %11, %13, 0;\n\t"
+      "addc.cc.u32     %12, %14, 0;\n\t"
+      "addc.cc.u32     %13, %15, 0;\n\t"
+      "madc.lo.cc.u32  %14, %16, %17, 0;\n\t"
+      "madc.hi.u32  %15, %16, %17, 0;\n\t"
+      "}"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(u.w[7]), "r"(bi));
+}
+
+
 template <class M>
-__device__ __forceinline__ Fe mont_sqr(const Fe& a) { return mont_mul<M>(a, a); }
+__device__ __forceinline__ Fe mont_sqr_lazy(const Fe& a) {
+  Fe u;                                              // words of 2a (a < 2^255)
+  u.w[0] = a.w[0] << 1;
+#pragma unroll
+  for (int k = 1; k < 8; k++) u.w[k] = (a.w[k] << 1) | (a.w[k - 1] >> 31);
+  uint32_t ev[8], od[8];
+  {
+    Fe u0 = u; u0.w[0] = a.w[0]; u0.w[1] = a.w[1] << 1;
+    mont_row_first<M>(ev, od, u0, a.w[0]);
+  }
+  mont_row_redc<M>(ev, od);
+#define ZC_SQR_ROW(I, X, Y) { Fe ui = u; ui.w[I] = a.w[I]; if (I + 1 < 8) ui.w[(I + 1) & 7] = a.w[(I + 1) & 7] << 1; sqr_row_##I(X, Y, ui, a.w[I]); mont_row_redc<M>(X, Y); }
+  ZC_SQR_ROW(1, od, ev) ZC_SQR_ROW(2, ev, od) ZC_SQR_ROW(3, od, ev) ZC_SQR_ROW(4, ev, od)
+  ZC_SQR_ROW(5, od, ev) ZC_SQR_ROW(6, ev, od) ZC_SQR_ROW(7, od, ev)
+#undef ZC_SQR_ROW
+  // as in mont_mul_lazy: result word k = ev[k] + od[k+1]
+  Fe r;
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32    %7, %15, 0;\n\t"
+      : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+      : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+  return r;
+}
+// r = a^2 / R mod m, canonical for a < 2m
+template <class M>
+__device__ __forceinline__ Fe mont_sqr(const Fe& a) {
+  Fe r = mont_sqr_lazy<M>(a);
+  reduce_once<M>(r);
+  return r;
+}
 
 template <class M>
 __device__ __forceinline__ Fe to_mont(const Fe& a) { return mont_mul<M>(a, Consts<M>::R2()); }

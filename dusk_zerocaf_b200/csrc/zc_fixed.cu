@@ -46,7 +46,7 @@ __device__ Fe fx_invert(const Fe& a) {
   Fe r = a;
 #pragma unroll 1
   for (int bit = 251; bit >= 0; bit--) {
-    r = fx_mul(r, r);
+    r = mont_sqr<ModP>(r);
     if ((e[bit >> 5] >> (bit & 31)) & 1u) r = fx_mul(r, a);
   }
   return r;

@@ -224,16 +224,17 @@ constexpr int SM_FAST_TPB = 128;
 // One out-of-line multiplier keeps the window loop (a doubling and an addition, 16 products) at a few KB of code instead
 // of ~60 KB of inlined carry chains: with 16 warps per SM spread over the loop, instruction fetch was a visible stall.
 __device__ __noinline__ Fe smf_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
+__device__ __noinline__ Fe smf_sqr(Fe a) { return mont_sqr<ModP>(a); }     // dedicated squaring: 36 + 32 wide multiplies
 // need_t == false: the caller's next operation is a doubling, which reads X, Y, Z only -- T3 = E H is skipped (the T of the
 // returned point is then stale).  Three of the four doublings of a window and every window addition but the last run that
 // way: 36 instead of 40 products per window.  need_t is uniform over the grid (a loop counter), never a divergent branch.
 __device__ __forceinline__ Pt smf_double(const Pt& p, bool need_t) {           // pt_double_fast (dbl-2008-hwcd, a = -1)
   typedef ModP M;
-  Fe A = smf_mul(p.X, p.X), B = smf_mul(p.Y, p.Y), Z2 = smf_mul(p.Z, p.Z);
+  Fe A = smf_sqr(p.X), B = smf_sqr(p.Y), Z2 = smf_sqr(p.Z);
   Fe C = fe_add<M>(Z2, Z2);
   Fe D = fe_neg<M>(A);
   Fe S = fe_add<M>(p.X, p.Y);
-  Fe E = fe_sub<M>(fe_sub<M>(smf_mul(S, S), A), B);
+  Fe E = fe_sub<M>(fe_sub<M>(smf_sqr(S), A), B);
   Fe G = fe_add<M>(D, B);
   Fe F = fe_sub<M>(G, C);
   Fe H = fe_sub<M>(D, B);

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128) msm_prep_affine_kernel(const uint64_t* __
   Fe zi = p.Z;
 #pragma unroll 1
   for (int bit = 251; bit >= 0; bit--) {
-    zi = prep_mul(zi, zi);
+    zi = mont_sqr<ModP>(zi);
     if ((e[bit >> 5] >> (bit & 31)) & 1u) zi = prep_mul(zi, p.Z);
   }
   const Fe x = prep_mul(p.X, zi), y = prep_mul(p.Y, zi);
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128) msm_fixed_base_table_kernel(const uint64_
     Fe zi = p.Z;
 #pragma unroll 1
     for (int bit = 251; bit >= 0; bit--) {
-      zi = prep_mul(zi, zi);
+      zi = mont_sqr<ModP>(zi);
       if ((e[bit >> 5] >> (bit & 31)) & 1u) zi = prep_mul(zi, p.Z);
     }
     const Fe x = prep_mul(p.X, zi), y = prep_mul(p.Y, zi);

@@ -27,6 +27,8 @@ __device__ __forceinline__ Fe modulus() { return Fe{{M::M0, M::M1, M::M2, M::M3,
 
 template <class M>
 __device__ __noinline__ Fe vmul(Fe a, Fe b) { return mont_mul<M>(a, b); }
+template <class M>
+__device__ __noinline__ Fe vsqr(Fe a) { return mont_sqr<M>(a); }
 
 // a^e mod m, left-to-right over the 253 exponent bits (0^0 = 1 as in the reference: the loop never runs)
 template <class M>
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(TPB) pow_kernel(const uint64_t* __restrict__ a
   Fe r = Consts<M>::R1();
 #pragma unroll 1
   for (int bit = 252; bit >= 0; bit--) {
-    r = vmul<M>(r, r);
+    r = vsqr<M>(r);
     uint32_t word = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) if ((bit >> 5) == k) word = ex.w[k];
