@@ -390,9 +390,9 @@ def run_b200(args):
             "implied_point_adds_per_s_strict": 374.0 * N_SMUL * world * 2 / (ms_strict * 1e-3),
             "roofline_int_strict": roofline_int(374 * 12 * 104, N_SMUL * 2 / (ms_strict * 1e-3),
                                                 "reference schedule: 249 doublings + ~125 additions, each the 12-product limb-exact Add; per GPU"),
-            "roofline_int_fast": roofline_int((63 * 8 + 189 * 7 + 63 * 7 + 8 + 64) * 104, N_SMUL * 2 / (ms_fast * 1e-3),
-                                              "4-bit signed windows: 252 dedicated doublings (63 with T: 4M+4S, 189 without: 3M+4S) + 64 cached additions "
-                                              "(7 products, the last 8) + the 8-entry table (64); per GPU")}
+            "roofline_int_fast": roofline_int((63 * 4 + 189 * 3 + 63 * 7 + 8 + 64) * 104 + 252 * 4 * 76, N_SMUL * 2 / (ms_fast * 1e-3),
+                                              "4-bit signed windows: 252 dedicated doublings (4 squarings of 68 + 8 multiplies each, plus 4 products when T is "
+                                              "needed -- 63 of them -- else 3) + 64 cached additions (7 products, the last 8) + the 8-entry table (64); per GPU")}
         # ---- config 5: MSM, strong scaling over the N ranks (bucket-window sharding + one exchange) ----------------------
         # Three modes, same scalars: plain (arbitrary points, operand pass inside the call), prepared generators (handle,
         # Z = 1 cached operands), fixed-base tables (handle, pre-scaled rows).  At N > 1 every mode is ALSO timed on one GPU

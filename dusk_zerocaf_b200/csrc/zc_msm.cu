@@ -41,13 +41,50 @@ __device__ __forceinline__ Fe DINV_MONT() {
   return Fe{{0x69c50bb0u, 0xa53327e2u, 0x96b47422u, 0xeaa0ffd5u, 0xfd35fb8fu, 0xd34f1e03u, 0x8d35344bu, 0x0b7245f4u}};
 }
 // ---- prep ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) msm_prep_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
-  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+// points (ABI layout, 160 B) -> cached operands (Y+X, Y-X, Z, 2dT), 128 B.  One warp converts 32 consecutive points: the
+// 5120 input bytes are read as 320 coalesced 16-byte loads into a per-warp shared-memory tile (176-byte point stride, so a
+// lane's 8-byte limb reads spread over the banks), and the 4096 output bytes leave through the same tile as coalesced
+// 16-byte stores.  The round-1 kernel read its point with twenty 8-byte loads at 160-byte stride and wrote 16-byte pieces
+// at 128-byte stride (32 sectors per request either way): 97 us for 2^20 points against ~55 us of HBM time.
+__global__ void __launch_bounds__(256) msm_prep_simple_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;              // fallback for a point array that is not 16-byte aligned
   if (i >= n) return;
-  Pt p = pt_load52(points + 20 * i);
-  PtCached c = pt_to_cached(p);
+  PtCached c = pt_to_cached(pt_load52(points + 20 * i));
   uint32_t* o = cached + 32 * i;
   st_fe(o, c.YpX); st_fe(o + 8, c.YmX); st_fe(o + 16, c.Z); st_fe(o + 24, c.T2d);
+}
+constexpr int PREP_TPB = 128, PREP_STRIDE16 = 11;              // tile: 32 points x 11 uint4 per warp
+__global__ void __launch_bounds__(PREP_TPB) msm_prep_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
+  __shared__ __align__(16) uint4 tile[PREP_TPB / 32][32 * PREP_STRIDE16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t base = ((size_t)blockIdx.x * (PREP_TPB / 32) + warp) * 32;          // first point of this warp
+  if (base >= n) return;
+  const size_t cnt = n - base < 32 ? n - base : 32;
+  uint4* t = tile[warp];
+  const uint4* src = reinterpret_cast<const uint4*>(points + 20 * base);
+#pragma unroll
+  for (int k = 0; k < 10; k++) {
+    const int j = lane + 32 * k;                                                   // 16-byte piece j of the warp's 320
+    if ((size_t)j < cnt * 10) t[(j / 10) * PREP_STRIDE16 + (j % 10)] = __ldg(src + j);
+  }
+  __syncwarp();
+  PtCached c;
+  if ((size_t)lane < cnt) c = pt_to_cached(pt_load52(reinterpret_cast<const uint64_t*>(t + lane * PREP_STRIDE16)));
+  __syncwarp();
+  if ((size_t)lane < cnt) {
+    uint4* o = t + lane * 8;                                                       // output tile: 128-byte stride
+    o[0] = make_uint4(c.YpX.w[0], c.YpX.w[1], c.YpX.w[2], c.YpX.w[3]); o[1] = make_uint4(c.YpX.w[4], c.YpX.w[5], c.YpX.w[6], c.YpX.w[7]);
+    o[2] = make_uint4(c.YmX.w[0], c.YmX.w[1], c.YmX.w[2], c.YmX.w[3]); o[3] = make_uint4(c.YmX.w[4], c.YmX.w[5], c.YmX.w[6], c.YmX.w[7]);
+    o[4] = make_uint4(c.Z.w[0], c.Z.w[1], c.Z.w[2], c.Z.w[3]);         o[5] = make_uint4(c.Z.w[4], c.Z.w[5], c.Z.w[6], c.Z.w[7]);
+    o[6] = make_uint4(c.T2d.w[0], c.T2d.w[1], c.T2d.w[2], c.T2d.w[3]); o[7] = make_uint4(c.T2d.w[4], c.T2d.w[5], c.T2d.w[6], c.T2d.w[7]);
+  }
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(cached + 32 * base);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int j = lane + 32 * k;
+    if ((size_t)j < cnt * 8) dst[j] = t[j];
+  }
 }
 
 // prepared points: normalise to Z = 1 first (one inversion per point, paid once per point set), so that every later
@@ -531,13 +568,20 @@ __global__ void __launch_bounds__(ACC_TPB, 512 / ACC_TPB) msm_accum_kernel(const
   const uint32_t start = s * (uint32_t)seg;
   if (start >= nnz) return;
   const uint32_t end = min(start + (uint32_t)seg, nnz);
-  {
+  if ((seg & 3) == 0) {
     const uint4* src = reinterpret_cast<const uint4*>(sorted + wl * n_pad + start);
 #pragma unroll 2
     for (int j = 0; j < seg / 4; j++) {
       uint4 v = src[j];
       idx_s[(4 * j + 0) * ACC_TPB + tx] = v.x; idx_s[(4 * j + 1) * ACC_TPB + tx] = v.y;
       idx_s[(4 * j + 2) * ACC_TPB + tx] = v.z; idx_s[(4 * j + 3) * ACC_TPB + tx] = v.w;
+    }
+  } else {                                   // even segment lengths that are not multiples of four (wave-filling lengths such as 14)
+    const uint2* src = reinterpret_cast<const uint2*>(sorted + wl * n_pad + start);
+#pragma unroll 2
+    for (int j = 0; j < seg / 2; j++) {
+      uint2 v = src[j];
+      idx_s[(2 * j + 0) * ACC_TPB + tx] = v.x; idx_s[(2 * j + 1) * ACC_TPB + tx] = v.y;
     }
   }
   uint32_t e_cur = idx_s[tx];
@@ -808,7 +852,11 @@ __device__ __forceinline__ Fe quad_block_tree(Fe acc, int n, int j, int q, int q
 
 // stage 2a: one block of C2A_QUADS quads per marginal sum.  Tasks of a window: M1[2^a1] and M0[32] over the window's
 // nblk blocks, then M2[2^a2] and M3[2^a3] over the block totals (block index = k3 2^a2 + k2).  marg: [M1 | M0 | M2 | M3].
-constexpr int C2A_QUADS = 64;
+// C2A_QUADS = 64 when the reduction has the GPU to itself (last group, fixed-base path); 32 for a group whose reduction runs
+// beside the next group's accumulation: a full wave of accumulation CTAs (4 x 128 threads x 104 registers per SM) leaves
+// 12 K registers per SM -- a 128-thread block of this kernel fits, a 256-thread block waits for the accumulation to END
+// (measured at 8 ranks, rank 0: the 240-doubling chain behind it started 140 us late).
+template <int C2A_QUADS>
 __global__ void __launch_bounds__(4 * C2A_QUADS) msm_cube2a_kernel(const uint32_t* __restrict__ tot, const uint32_t* __restrict__ pm1,
                                                                    const uint32_t* __restrict__ pm0, int a1, int a2, int a3, int nwl,
                                                                    uint32_t* __restrict__ marg) {
@@ -1162,6 +1210,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       for (int i = 0; i < 3; i++) ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_hi[i], cudaStreamNonBlocking, prio_hi));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, prio_hi));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sort_stream, cudaStreamNonBlocking, prio_lo));
+      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sort_hi, cudaStreamNonBlocking, prio_hi));
       for (int i = 0; i < 16; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     }
     // st: digits, sort, accumulation.  sides[g % 4]: operand preparation (sides[0]), then stitch + reduce of group g --
@@ -1215,10 +1264,16 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       if (sort_atomic) ZC_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nwb * nb * 4, st));
       ZC_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, 256 * MAX_GROUPS, st));
       if (!use_prepared && !use_fb) {
+        // The operand pass streams 288 bytes per point through HBM, the first group's sort is latency-bound: they share the
+        // GPU well, but only if the sort's few hundred blocks are not queued behind the pass's 8192 -- the pass goes to the
+        // low-priority side stream, the sort (sharded: sort_hi) above it.  Both must finish before the first accumulation.
+        cudaStream_t ps = ctx->side_stream;
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-        ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[0], 0));
-        msm_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, side>>>(points, cached, n); nlaunch++; mark(side, 1, "msm_prep_kernel");
-        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[1], side));
+        ZC_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->ev[0], 0));
+        if (((uintptr_t)points & 15) == 0) msm_prep_kernel<<<(unsigned)((n + PREP_TPB - 1) / PREP_TPB), PREP_TPB, 0, ps>>>(points, cached, n);
+        else msm_prep_simple_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ps>>>(points, cached, n);
+        nlaunch++; mark(ps, 1, "msm_prep_kernel");
+        ZC_CUDA(ctx, cudaEventRecord(ctx->ev[1], ps));
       }
       // digits + histogram, scan, scatter of the local windows [lo, hi) on stream s_
       auto sort_windows = [&](cudaStream_t s_, int sid, int lo, int hi) {
@@ -1277,11 +1332,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       static const bool pipe_sort_env = !(getenv("ZC_MSM_PIPE_SORT") && atoi(getenv("ZC_MSM_PIPE_SORT")) == 0);
       const bool pipe_sort = pipe_sort_env && !use_fb && ngroups > 1;
       if (pipe_sort) {
+        // sharded (few windows per rank, everything on the critical path): high priority; one GPU: low, under the accumulations
+        cudaStream_t ss = nranks > 1 ? ctx->sort_hi : ctx->sort_stream;
         ZC_CUDA(ctx, cudaEventRecord(ctx->ev[15], st));
-        ZC_CUDA(ctx, cudaStreamWaitEvent(ctx->sort_stream, ctx->ev[15], 0));
+        ZC_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev[15], 0));
         for (int g = 0; g < ngroups; g++) {
-          sort_windows(ctx->sort_stream, 3, glo[g], ghi[g]);
-          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[11 + g], ctx->sort_stream));
+          sort_windows(ss, 3, glo[g], ghi[g]);
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[11 + g], ss));
         }
       } else {
         sort_windows(st, 0, 0, nwl);
@@ -1333,7 +1390,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
           else { msm_stitch_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, tail>>>(src, buckets, (size_t)nb); nlaunch++; mark(tail, tid_, "msm_stitch_kernel"); }
           msm_cube1_quad_kernel<<<(unsigned)nblk, 256, 0, tail>>>(buckets, btot, pm1, pm0, parts > 1 ? offs : nullptr, hist, lim_lo, lim_hi); nlaunch++; mark(tail, tid_, "msm_cube1_quad_kernel");
         }
-        msm_cube2a_kernel<<<(unsigned)ntask, 4 * C2A_QUADS, 0, tail>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(tail, tid_, "msm_cube2a_kernel");
+        msm_cube2a_kernel<64><<<(unsigned)ntask, 256, 0, tail>>>(btot, pm1, pm0, a1, a2, a3, 1, marg); nlaunch++; mark(tail, tid_, "msm_cube2a_kernel");
         msm_cube2b_kernel<<<4, 128, 0, tail>>>(marg, a1, a2, a3, -1, comp); nlaunch++; mark(tail, tid_, "msm_cube2b_kernel");
         ChainGaps gaps;
         for (int i = 0; i < MAX_WINDOWS; i++) gaps.pre[i] = 0;
@@ -1354,8 +1411,20 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         if (pipe_sort) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[11 + g], 0));                 // this group's entries are sorted
         size_t group_entries = 0;
         for (int wl = lo; wl < hi; wl++) group_entries += tasks[wl].p1 - tasks[wl].p0;
-        const int seg = group_entries >= ((size_t)1 << 22) ? 32 : (group_entries > ((size_t)1 << 19) ? 16 : 8);
-        const int nseg = (int)(n_pad / seg);
+        int seg = group_entries >= ((size_t)1 << 22) ? 32 : (group_entries > ((size_t)1 << 19) ? 16 : 8);
+        // A launch that fits one wave of the 4 x 128-thread slots per SM runs as long as its busiest SM: with 2^20 entries in
+        // 16-entry segments 512 CTAs land on 592 slots (68 SMs hold four CTAs, 80 hold three) and every thread does 16
+        // additions; 14-entry segments give 586 CTAs -- four on every SM -- of 14 additions each.  ZC_MSM_SEG forces a length.
+        {
+          static const int seg_env = getenv("ZC_MSM_SEG") ? atoi(getenv("ZC_MSM_SEG")) : 0;
+          const size_t slots = (size_t)4 * ctx->sm_count * 128;
+          if (seg_env >= 2 && seg_env <= SEG_MAX && (seg_env & 1) == 0) seg = seg_env;
+          else if (seg_env == 0 && group_entries / seg <= slots && group_entries > slots * 8) {
+            const int fill = 2 * (int)((group_entries + 2 * slots - 1) / (2 * slots));      // smallest even length whose grid fits the slots
+            if (fill >= 8 && fill < seg) seg = fill;
+          }
+        }
+        const int nseg = (int)((n_pad + seg - 1) / seg);
         const size_t tot = (size_t)gsz * nb;
         const size_t tseg = (size_t)gsz * nseg;
         const uint32_t *g_sorted = sorted + (size_t)lo * n_pad, *g_offs = offs + (size_t)lo * nb, *g_hist = hist + (size_t)lo * nb;
@@ -1426,9 +1495,13 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
           ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
           ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
         }
-        msm_cube2a_kernel<<<(unsigned)((size_t)gsz * ntask), 4 * C2A_QUADS, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
-            pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz,
-            marg + 32 * ((size_t)lo * ntask)); nlaunch++; mark(side, 1, "msm_cube2a_kernel");
+        if (g == ngroups - 1)
+          msm_cube2a_kernel<64><<<(unsigned)((size_t)gsz * ntask), 256, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz, marg + 32 * ((size_t)lo * ntask));
+        else
+          msm_cube2a_kernel<32><<<(unsigned)((size_t)gsz * ntask), 128, 0, side>>>(btot + 32 * ((size_t)lo * nblk),
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), a1, a2, a3, gsz, marg + 32 * ((size_t)lo * ntask));
+        nlaunch++; mark(side, 1, "msm_cube2a_kernel");
         msm_cube2b_kernel<<<4 * gsz, 128, 0, side>>>(marg + 32 * ((size_t)lo * ntask), a1, a2, a3, drop_wl, comp + 128 * (size_t)lo); nlaunch++; mark(side, 1, "msm_cube2b_kernel");
         // only the top local window of the whole MSM can be short, i.e. the first window of the first group
         const int drop0 = (drop_wl == gsz - 1) ? A0 : 0;
