@@ -8,7 +8,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libzerocaf_b200.so")
+# ZC_LIB_PATH: an alternative build of the same library (A/B runs of kernel variants); default: the in-tree build
+SO_PATH = os.environ.get("ZC_LIB_PATH") or os.path.join(_HERE, "libzerocaf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "zerocaf_b200.h")
 
 _u64p = ctypes.c_void_p   # pointers are passed as integers (host numpy .ctypes.data or device data_ptr())
