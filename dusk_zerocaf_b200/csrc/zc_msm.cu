@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(ACC_TPB, 512 / ACC_TPB) msm_accum_kernel(const
 // Buckets with at most FIX_INLINE partials are stitched on the fly by whoever reads them (load_bucket, used by the
 // first reduction stage); heavier ones are queued here for msm_heavy_kernel (one warp per bucket, tree sum), which
 // writes them into buckets[].
-static const int FIX_INLINE = getenv("ZC_MSM_FIX_INLINE") ? atoi(getenv("ZC_MSM_FIX_INLINE")) : 6;       // per-window buckets; the merged buckets of the fixed-base path choose theirs per call
+static const int FIX_INLINE = getenv("ZC_MSM_FIX_INLINE") ? atoi(getenv("ZC_MSM_FIX_INLINE")) : 8;       // per-window buckets; the merged buckets of the fixed-base path choose theirs per call
 __global__ void __launch_bounds__(256) msm_fixq_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
                                                        int seg, int nwl, int nb, int fix_inline, uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list,
                                                        long long lim_lo, long long lim_hi) {
@@ -715,7 +715,7 @@ __device__ __forceinline__ Pt warp_sum_pt(Pt v) {
   return v;
 }
 
-__global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
+__global__ void __launch_bounds__(128, 5) msm_heavy_kernel(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hist,
                                                         int nseg, int seg, int nb, const uint32_t* __restrict__ partH,
                                                         const uint32_t* __restrict__ partT, uint32_t* __restrict__ buckets,
                                                         const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
@@ -1034,6 +1034,47 @@ __global__ void __launch_bounds__(256) msm_cube1_quad_kernel(const uint32_t* __r
   }
 }
 
+// The same stage in 128-thread blocks (32 quads) for a reduction that runs BESIDE the next group's accumulation: a full wave
+// of accumulation CTAs leaves 12 K registers per SM, so a 256-thread block of msm_cube1_quad_kernel waits until the
+// accumulation ends (rank 5 of 8: its high window's chain started 110 us late).  Warp w takes row w: every quad sums four
+// buckets of the row, the warp's eight quads finish the row in a three-level tree; then quad j sums column j, and quad 0
+// adds up the four row sums.  12 dependent additions instead of 8 -- used only where it overlaps.
+__global__ void __launch_bounds__(128) msm_cube1_quad32_kernel(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ tot,
+                                                               uint32_t* __restrict__ pm1, uint32_t* __restrict__ pm0) {
+  __shared__ __align__(16) uint32_t sv[128 * 32];               // the block's buckets
+  __shared__ __align__(16) uint32_t sw[32 * 32];                // row trees, then the four row sums
+  const int q = threadIdx.x & 3, qbase = threadIdx.x & 28, j = threadIdx.x >> 2, row = threadIdx.x >> 5, qi = j & 7;
+  const size_t blk = blockIdx.x;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(buckets + 32 * (blk * 128));
+    uint4* dst = reinterpret_cast<uint4*>(sv);
+    for (int k = threadIdx.x; k < 128 * 8; k += 128) dst[k] = src[k];
+  }
+  __syncthreads();
+  Fe acc = ld_coord(sv + 32 * (row * 32 + 4 * qi), q);
+  for (int t = 1; t < 4; t++) acc = quad_add(acc, ld_pt(sv + 32 * (row * 32 + 4 * qi + t)), q, qbase);
+  for (int s = 4; s >= 1; s >>= 1) {
+    if (qi < 2 * s) st_coord(sw + 32 * j, q, acc);
+    __syncwarp();
+    const bool on = qi < s;
+    const Fe t = quad_add(acc, ld_pt(sw + 32 * (on ? j + s : j)), q, qbase);
+    if (on) acc = t;
+    __syncwarp();
+  }
+  if (qi == 0) st_coord(pm1 + 32 * (blk * 4 + row), q, acc);
+  __syncthreads();                                               // every warp is done with its part of sw
+  if (qi == 0) st_coord(sw + 32 * row, q, acc);
+  Fe cs = ld_coord(sv + 32 * j, q);                              // column j
+  for (int k = 1; k < 4; k++) cs = quad_add(cs, ld_pt(sv + 32 * (k * 32 + j)), q, qbase);
+  st_coord(pm0 + 32 * (blk * 32 + j), q, cs);
+  __syncthreads();
+  if (row == 0) {                                                // quad 0: block total from the four row sums
+    Fe t = ld_coord(sw, q);
+    for (int k = 1; k < 4; k++) t = quad_add(t, ld_pt(sw + 32 * k), q, qbase);
+    if (j == 0) st_coord(tot + 32 * blk, q, t);
+  }
+}
+
 // ---- window chain (four lanes per point operation, see the quad helpers above) ---------------------------------------
 // One warp.  acc (in/out, extended Montgomery words) is the running sum, already scaled to 2^(A0+a1+a2) times the unit
 // of this group's top window.  Each window contributes four components (msm_cube2b):
@@ -1161,7 +1202,15 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     size_t o_hist = o;   o = align_up(o + (size_t)nwb * nb * 4, 256);
     size_t o_offs = o;   o = align_up(o + (size_t)nwb * nb * 4, 256);
     size_t o_ranks = o;  o = align_up(o + (sort_atomic ? (size_t)nwl * n * 4 : 0), 256);      // sort A only: rank of each entry inside its bucket
-    const int sort_cb = sort_coarse_bits(c - 1, use_fb ? fb_entries : n, nwb), sort_fb = c - 1 - sort_cb;
+    // A spread short window (fixed-base path) only reaches the lower half of the merged bucket range: those bins take 1.5x the
+    // average (2^20 points, rank 0 of 8: 12288 entries per 128-bucket bin, over the 9216 a msm_sort_fine block stages in shared
+    // memory -> its slow path, 21 instead of 11 us).  Plan the bins for the heavier half.
+    // The same holds for a sub-bucketed short window of the per-window paths when the scalars do not reach its top digit bit
+    // (250-bit windows of scalars below L ~ 2^249: half of its slots stay empty, the other half hold twice the average).
+    bool skewed = false;
+    for (int t = 0; t < nwl; t++) skewed |= use_fb ? merged_spread_bits(c, tasks[t].w) > 0 : short_window_sub_bits(c, tasks[t].w) > 0;
+    const size_t sort_entries = use_fb ? fb_entries : n;
+    const int sort_cb = sort_coarse_bits(c - 1, skewed ? 2 * sort_entries : sort_entries, nwb), sort_fb = c - 1 - sort_cb;
     const int sort_nblk = (int)((n + SORT_TPB - 1) / SORT_TPB) < 4 * ctx->sm_count ? (int)((n + SORT_TPB - 1) / SORT_TPB) : 4 * ctx->sm_count;
     if (sort_nblk > 32 * BSCAN_PER) return zc_fail(ctx, ZC_ERR_STATE, "device has more SMs than the MSM sort plans for");
     size_t o_scount = o; o = align_up(o + ((size_t)nwb << sort_cb) * sort_nblk * 4, 256);
@@ -1498,7 +1547,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
           }
         }
         const size_t cube_smem = (size_t)(8 * nw1 * 32 + 8 * nw1) * sizeof(uint4);
-        if (quad_stage1) {
+        if (quad_stage1 && !seq1 && g < ngroups - 1 && nranks > 1) {   // beside the next accumulation (see msm_cube1_quad32_kernel)
+          msm_cube1_quad32_kernel<<<(unsigned)((size_t)gsz * nblk), 128, 0, s1>>>(g_buckets, btot + 32 * ((size_t)lo * nblk),
+              pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(s1, s1id, "msm_cube1_quad32_kernel");
+        } else if (quad_stage1) {
           msm_cube1_quad_kernel<<<(unsigned)((size_t)gsz * nblk), 256, 0, s1>>>(g_buckets, btot + 32 * ((size_t)lo * nblk),
               pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32), nullptr, nullptr, LIM_ALL_LO, LIM_ALL_HI); nlaunch++; mark(s1, s1id, "msm_cube1_quad_kernel");
         } else {
