@@ -1180,7 +1180,21 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     const int nwb = use_fb ? 1 : nwl;                           // bucket sets
     wmap.merged = use_fb ? 1 : 0;
     const size_t fb_entries = (size_t)nwl * n;
-    const int fb_seg = fb_entries >= ((size_t)1 << 22) ? 32 : (fb_entries > ((size_t)1 << 19) ? 16 : 8);
+    // Segment length of an accumulation launch over `entries` sorted entries.  Default by amount of work (32 / 16 / 8); but a
+    // launch that can go out as ONE full wave of the 4 x 128-thread slots per SM does: it runs as long as its busiest SM, so
+    // 2^20 entries are 586 CTAs of 14-entry segments (four on every SM) rather than 512 CTAs of 16 (68 SMs with four, 80 with
+    // three), and 2^21 entries 585 CTAs of 28 rather than 1024 of 16 (measured per rank of eight: 0.557 -> 0.533 ms prepared,
+    // 0.392 -> 0.389 ms with tables).  ZC_MSM_SEG forces a length (even, 8..32).
+    static const int seg_env = getenv("ZC_MSM_SEG") ? atoi(getenv("ZC_MSM_SEG")) : 0;
+    auto pick_seg = [&](size_t entries) -> int {
+      if (seg_env >= 8 && seg_env <= SEG_MAX && (seg_env & 1) == 0) return seg_env;
+      int seg = entries >= ((size_t)1 << 22) ? 32 : (entries > ((size_t)1 << 19) ? 16 : 8);
+      const size_t slots = (size_t)4 * ctx->sm_count * 128;
+      const int fill = 2 * (int)((entries + 2 * slots - 1) / (2 * slots));          // smallest even length whose grid fits one wave
+      if (fill >= 8 && fill <= SEG_MAX) seg = fill;
+      return seg;
+    };
+    const int fb_seg = pick_seg(fb_entries);
     // ZC_MSM_SORT=atomic: the round-1 sort (one global histogram atomic per entry); default: the two-level counting sort
     static const bool sort_atomic = getenv("ZC_MSM_SORT") && !strcmp(getenv("ZC_MSM_SORT"), "atomic");
     // workspace layout
@@ -1192,7 +1206,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
     // per bucket (a 64-entry bucket spans 8-9 segments of 8 and would go to the one-warp-per-bucket heavy path), hence
     // not always 8.  The partial-slot arrays are laid out for the shortest segment.
     const size_t n_pad = align_up(use_fb ? fb_entries : n, SEG_MAX);
-    const int nseg_alloc = (int)(n_pad / (use_fb ? fb_seg : 8));
+    const int nseg_alloc = (int)(n_pad / (use_fb ? fb_seg : 8)) + 1;
     size_t o_digits = o;                                        // sort A: digits (4 B per entry); sort B: coarse-sorted entries (8 B)
     o = align_up(o + ((size_t)nwl * n > (size_t)nwb * n_pad ? (size_t)nwl * n : (size_t)nwb * n_pad) * 8 + 256, 256);
     size_t o_sorted = o; o = align_up(o + (size_t)nwb * n_pad * 4 + 256, 256);
@@ -1410,7 +1424,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         // one bucket set over all (window, point) entries: accumulate, stitch, reduce, combine the four cube components
         // (A0 + a1 + a2 doublings in all).  A typical bucket spans entries / (nb seg) segments; up to twice that is stitched
         // inline by the reduction's loads, the few heavier ones (buckets the short top window also feeds) one warp each.
-        const int seg = fb_seg, nseg = (int)(n_pad / seg);
+        const int seg = fb_seg, nseg = (int)((n_pad + seg - 1) / seg);
         const int fix_inline = 2 * (int)(fb_entries / ((size_t)nb * seg)) + FIX_INLINE;
         // Split accumulation (experiment, ZC_MSM_SPLIT=2..4; off by default): the sorted list is accumulated by `parts` launches
         // over consecutive segment ranges (each on its own stream, the block scheduler drains the earlier launch first) and the
@@ -1474,19 +1488,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         if (pipe_sort) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[11 + g], 0));                 // this group's entries are sorted
         size_t group_entries = 0;
         for (int wl = lo; wl < hi; wl++) group_entries += tasks[wl].p1 - tasks[wl].p0;
-        int seg = group_entries >= ((size_t)1 << 22) ? 32 : (group_entries > ((size_t)1 << 19) ? 16 : 8);
-        // A launch that fits one wave of the 4 x 128-thread slots per SM runs as long as its busiest SM: with 2^20 entries in
-        // 16-entry segments 512 CTAs land on 592 slots (68 SMs hold four CTAs, 80 hold three) and every thread does 16
-        // additions; 14-entry segments give 586 CTAs -- four on every SM -- of 14 additions each.  ZC_MSM_SEG forces a length.
-        {
-          static const int seg_env = getenv("ZC_MSM_SEG") ? atoi(getenv("ZC_MSM_SEG")) : 0;
-          const size_t slots = (size_t)4 * ctx->sm_count * 128;
-          if (seg_env >= 2 && seg_env <= SEG_MAX && (seg_env & 1) == 0) seg = seg_env;
-          else if (seg_env == 0 && group_entries / seg <= slots && group_entries > slots * 8) {
-            const int fill = 2 * (int)((group_entries + 2 * slots - 1) / (2 * slots));      // smallest even length whose grid fits the slots
-            if (fill >= 8 && fill < seg) seg = fill;
-          }
-        }
+        const int seg = pick_seg(group_entries);
         const int nseg = (int)((n_pad + seg - 1) / seg);
         const size_t tot = (size_t)gsz * nb;
         const size_t tseg = (size_t)gsz * nseg;
