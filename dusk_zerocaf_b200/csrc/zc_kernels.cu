@@ -259,11 +259,19 @@ __device__ __forceinline__ Pt smf_add(const Pt& p, const PtCached& q, bool need_
   if (need_t) r.T = ZC_SMF_OUT(1, E, H);
   return r;
 }
-__global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const uint64_t* __restrict__ points,
+// SMEM_TABLE (experiment, ZC_SMF_SMEM=1): the per-thread table in shared memory instead of the global arena.  1 KiB per thread
+// means ONE 128-thread CTA per SM (128 KiB) -- 4 warps per SM instead of 16; measured 2^20 scalar multiplications in
+// profiles/r02_fixed_base_tma_ab.txt.  The product keeps the coalesced global arena (L2-resident, registers-limited occupancy).
+template <bool SMEM_TABLE>
+__global__ void __launch_bounds__(SM_FAST_TPB, SMEM_TABLE ? 1 : 4) scalar_mul_fast_kernel(const uint64_t* __restrict__ points,
                                                                          const uint64_t* __restrict__ scalars,
                                                                          uint64_t* __restrict__ out, size_t n,
-                                                                         uint4* __restrict__ table, size_t nslots) {
-  const size_t slot = (size_t)blockIdx.x * SM_FAST_TPB + threadIdx.x;
+                                                                         uint4* __restrict__ table_g, size_t nslots_g) {
+  extern __shared__ __align__(16) uint4 smf_smem[];
+  const size_t slot_g = (size_t)blockIdx.x * SM_FAST_TPB + threadIdx.x;
+  uint4* const table = SMEM_TABLE ? smf_smem : table_g;
+  const size_t nslots = SMEM_TABLE ? (size_t)SM_FAST_TPB : nslots_g;             // table stride
+  const size_t slot = SMEM_TABLE ? (size_t)threadIdx.x : slot_g;                 // table slot
   auto store_entry = [&](int e, const PtCached& c) {
     uint4* base = table + (size_t)e * 8 * nslots + slot;
     base[0 * nslots] = make_uint4(c.YpX.w[0], c.YpX.w[1], c.YpX.w[2], c.YpX.w[3]); base[1 * nslots] = make_uint4(c.YpX.w[4], c.YpX.w[5], c.YpX.w[6], c.YpX.w[7]);
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(SM_FAST_TPB, 4) scalar_mul_fast_kernel(const u
     load_fe(base, c.YpX); load_fe(base + 2 * nslots, c.YmX); load_fe(base + 4 * nslots, c.Z); load_fe(base + 6 * nslots, c.T2d);
     return c;
   };
-  for (size_t i = slot; ; i += nslots) {
+  for (size_t i = slot_g; ; i += nslots_g) {
     // whole warps leave together (the loop body uses warp votes)
     if (!__any_sync(0xffffffffu, i < n)) break;
     const bool live = i < n;
@@ -767,7 +775,14 @@ int32_t zc_point_scalar_mul_batch_dev(zc_ctx* ctx, const uint64_t* points, const
     void* table = nullptr;
     int32_t rc = zc_scratch(ctx, 5, nslots * 1024, &table);
     if (rc) return rc;
-    scalar_mul_fast_kernel<<<grid, SM_FAST_TPB, 0, ctx->stream>>>(points, scalars, out, n, (uint4*)table, nslots);
+    static const bool smem_table = getenv("ZC_SMF_SMEM") && atoi(getenv("ZC_SMF_SMEM")) != 0;
+    if (smem_table) {
+      static bool attr_set = false;
+      if (!attr_set) { ZC_CUDA(ctx, cudaFuncSetAttribute(scalar_mul_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_FAST_TPB * 1024)); attr_set = true; }
+      const unsigned g1 = grid < (unsigned)ctx->sm_count ? grid : (unsigned)ctx->sm_count;
+      scalar_mul_fast_kernel<true><<<g1, SM_FAST_TPB, SM_FAST_TPB * 1024, ctx->stream>>>(points, scalars, out, n, nullptr, (size_t)g1 * SM_FAST_TPB);
+    } else
+    scalar_mul_fast_kernel<false><<<grid, SM_FAST_TPB, 0, ctx->stream>>>(points, scalars, out, n, (uint4*)table, nslots);
   }
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
