@@ -415,6 +415,27 @@ def test_msm_edges(zc, oracle, kats):
     assert oracle.pt_eq(zc.batch.msm(pts, sc), oracle.pt_identity())
 
 
+@pytest.mark.parametrize("n", [31, 32, 33, 127, 129, 1025])
+def test_msm_operand_pass_shapes(zc, oracle, n):
+    """The operand pass converts 32 points per warp through a shared-memory tile (16-byte loads): ragged last tiles, and a
+    point array that is only 8-byte aligned (falls back to the element-wise pass).  Arbitrary points, device pointers."""
+    import torch
+    P = synth_points(oracle, 90, n)
+    s = oracle.synth_scalar(SEED, 91, 0, n)
+    want = oracle.msm_naive(P, s, threads=8)
+    ctx = zc.default_context()
+    dS = torch.from_numpy(s.view(np.int64)).cuda()
+    buf = torch.zeros(n * 20 + 2, dtype=torch.int64, device="cuda")       # cudaMalloc'd: 256-byte aligned
+    out = torch.zeros(20, dtype=torch.int64, device="cuda")
+    for off in (0, 1):                                                    # 0: 16-byte aligned, 1: 8 bytes off
+        view = buf[off:off + n * 20]
+        view.copy_(torch.from_numpy(P.view(np.int64).reshape(-1)))
+        assert (view.data_ptr() % 16 == 0) == (off == 0)
+        ctx.check(ctx._L.zc_msm_dev(ctx._h, view.data_ptr(), dS.data_ptr(), n, 16, out.data_ptr()))
+        ctx.sync()
+        assert oracle.pt_eq(out.cpu().numpy().view(np.uint64), want), (n, off)
+
+
 def test_msm_sharding_partials_fold_to_full(zc, oracle):
     """The multi-GPU decomposition without NCCL: partial points of ranks 0..R-1 folded in rank order == full MSM."""
     import torch
