@@ -1402,7 +1402,19 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       // Task groups, top-down (local index wl ascends with the window index)
       const int ngroups = nwl < MAX_GROUPS ? nwl : MAX_GROUPS;
       int glo[MAX_GROUPS], ghi[MAX_GROUPS];
-      for (int g = 0, h = nwl; g < ngroups; g++) { const int gsz = (h + (ngroups - g) - 1) / (ngroups - g); ghi[g] = h; glo[g] = h - gsz; h -= gsz; }
+      // Group sizes: equal.  (Experiment, ZC_MSM_GROUP_SPLIT=1: two pieces of the pipeline are exposed -- the sort of the FIRST
+      // group and the reduction + window chain of the LAST one -- so give the outer groups half the windows of the inner ones,
+      // 2, 6, 6, 2 instead of 4, 4, 4, 4 at 16 windows.  Measured at 2^20 points: 2.730 vs 2.666 ms prepared, 3.009 vs 2.957 ms
+      // arbitrary points on one GPU, 1.523 vs 1.448 ms for rank 1 of 2 -- the six-window accumulations lose more than the
+      // shorter ends gain.  Off.)
+      static const bool uneven_env = getenv("ZC_MSM_GROUP_SPLIT") && atoi(getenv("ZC_MSM_GROUP_SPLIT")) == 1;
+      int gsizes[MAX_GROUPS];
+      for (int g = 0, h = nwl; g < ngroups; g++) { gsizes[g] = (h + (ngroups - g) - 1) / (ngroups - g); h -= gsizes[g]; }
+      if (uneven_env && ngroups == 4 && nwl >= 8) {
+        const int k = nwl / 8, m = (nwl - 2 * k + 1) / 2;
+        gsizes[0] = k; gsizes[1] = m; gsizes[2] = nwl - 2 * k - m; gsizes[3] = k;
+      }
+      for (int g = 0, h = nwl; g < ngroups; g++) { ghi[g] = h; glo[g] = h - gsizes[g]; h -= gsizes[g]; }
       // The sort of a group is atomics / scattered stores, its accumulation is multiplier-bound: the groups' sorts run on
       // their own stream, one or more groups ahead of the accumulation (2^20 points on one GPU: 0.4 ms of sorting, three
       // quarters of it hidden).
