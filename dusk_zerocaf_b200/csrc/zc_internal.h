@@ -80,6 +80,7 @@ struct zc_ctx {
   // MSM: side stream for the window-scaling chain + events (created on first use)
   cudaStream_t side_stream = nullptr, side_extra[3] = {nullptr, nullptr, nullptr}, chain_stream = nullptr, sort_stream = nullptr;
   cudaStream_t side_hi[3] = {nullptr, nullptr, nullptr};   // high-priority twins of the first three side streams (sharded MSM)
+  cudaStream_t acc2 = nullptr;                            // second accumulation stream (ZC_MSM_ACC_OVERLAP: consecutive groups' accumulations back to back)
   cudaStream_t sort_hi = nullptr;                         // high-priority sort stream (sharded MSM: the first sort must not queue behind the operand pass)
   cudaEvent_t ev[16] = {};
 };

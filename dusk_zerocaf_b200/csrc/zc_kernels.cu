@@ -563,7 +563,7 @@ int32_t zc_ctx_destroy(zc_ctx* ctx) {
   if (ctx->peer_error_host) cudaFreeHost(ctx->peer_error_host);
   if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); for (int i = 0; i < 2 * ZC_PIPE_MAX_CHUNKS; i++) if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]); }
   if (ctx->msm_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->msm_graph_exec);
-  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); cudaStreamSynchronize(ctx->chain_stream); cudaStreamDestroy(ctx->chain_stream); for (int i = 0; i < 3; i++) { if (ctx->side_extra[i]) cudaStreamDestroy(ctx->side_extra[i]); if (ctx->side_hi[i]) cudaStreamDestroy(ctx->side_hi[i]); } if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream); if (ctx->sort_hi) cudaStreamDestroy(ctx->sort_hi); }
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); cudaStreamSynchronize(ctx->chain_stream); cudaStreamDestroy(ctx->chain_stream); for (int i = 0; i < 3; i++) { if (ctx->side_extra[i]) cudaStreamDestroy(ctx->side_extra[i]); if (ctx->side_hi[i]) cudaStreamDestroy(ctx->side_hi[i]); } if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream); if (ctx->sort_hi) cudaStreamDestroy(ctx->sort_hi); if (ctx->acc2) cudaStreamDestroy(ctx->acc2); }
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

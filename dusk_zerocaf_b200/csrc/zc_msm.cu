@@ -1287,6 +1287,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chain_stream, cudaStreamNonBlocking, prio_hi));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sort_stream, cudaStreamNonBlocking, prio_lo));
       ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sort_hi, cudaStreamNonBlocking, prio_hi));
+      ZC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->acc2, cudaStreamNonBlocking, prio_lo));
       for (int i = 0; i < 16; i++) ZC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     }
     // st: digits, sort, accumulation.  sides[g % 4]: operand preparation (sides[0]), then stitch + reduce of group g --
@@ -1497,7 +1498,14 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
       for (int g = 0; g < ngroups; g++) {
         side = (g == ngroups - 1) ? sides[3] : sides[g % 3];
         const int hi = ghi[g], lo = glo[g], gsz = hi - lo;
-        if (pipe_sort) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[11 + g], 0));                 // this group's entries are sorted
+        // ZC_MSM_ACC_OVERLAP=1 (experiment, off): consecutive groups accumulate on alternating streams, so the next group's CTAs
+        // could fill the slots the current group's last, partial wave leaves idle.  Measured: nothing on one GPU (2.659 vs
+        // 2.660 ms -- the next group's low-priority sort only finishes when the current accumulation ends, and the machine is
+        // throughput-bound: whatever runs beside an accumulation costs it about its own stand-alone time), worse for rank 0 of 8
+        // (0.612 vs 0.521 ms: the low window's CTAs delay the high window's reduction and its 240-doubling chain).
+        static const bool acc_overlap = getenv("ZC_MSM_ACC_OVERLAP") && atoi(getenv("ZC_MSM_ACC_OVERLAP")) == 1;
+        cudaStream_t as = (acc_overlap && pipe_sort && (g & 1)) ? ctx->acc2 : st;
+        if (pipe_sort) ZC_CUDA(ctx, cudaStreamWaitEvent(as, ctx->ev[11 + g], 0));                 // this group's entries are sorted
         size_t group_entries = 0;
         for (int wl = lo; wl < hi; wl++) group_entries += tasks[wl].p1 - tasks[wl].p0;
         const int seg = pick_seg(group_entries);
@@ -1510,14 +1518,14 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         if (g == 0 && !use_prepared) ZC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[1], 0));   // cached operands ready
         const int tpb = acc_tpb(tseg);
         if (use_prepared && tpb == 64)
-          msm_accum_kernel<true, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
+          msm_accum_kernel<true, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, as>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
         else if (use_prepared)
-          msm_accum_kernel<true, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
+          msm_accum_kernel<true, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, as>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
         else if (tpb == 64)
-          msm_accum_kernel<false, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
+          msm_accum_kernel<false, 64><<<(unsigned)((tseg + 63) / 64), 64, 0, as>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
         else
-          msm_accum_kernel<false, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, st>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
-        nlaunch++; mark(st, 0, "msm_accum_kernel");
+          msm_accum_kernel<false, 128><<<(unsigned)((tseg + 127) / 128), 128, 0, as>>>(cached, g_sorted, g_offs, g_hist, n_pad, nseg, seg, gsz, nb, g_buckets, g_partH, g_partT, 0u, (uint32_t)tseg);
+        nlaunch++; mark(as, as == st ? 0 : 4, "msm_accum_kernel");
         // everything after the accumulation is latency-bound (few warps, long dependent chains): it runs on the side
         // stream, under the next group's accumulation
         // Stage 1 of a reduction (stitch + the first trees) is wide: beside the next group's accumulation it competes for the
@@ -1531,10 +1539,10 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
         const int post_all = c * tasks[0].w;                     // doublings after the last group (the rank's lowest window)
         const bool seq1 = (g < ngroups - 1) && (seq_env >= 0 ? seq_env != 0 : (nranks > 1 && g == 0 && chain_after > 100));
         (void)post_all;
-        cudaStream_t s1 = seq1 ? st : side;
+        cudaStream_t s1 = seq1 ? as : side;
         const int s1id = seq1 ? 0 : 1;
         if (!seq1) {
-          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], as));
           ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
         }
         msm_fixq_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s1>>>(g_offs, g_hist, seg, gsz, nb, FIX_INLINE, g_hcount, g_hlist, LIM_ALL_LO, LIM_ALL_HI); nlaunch++; mark(s1, s1id, "msm_fixq_kernel");
@@ -1572,7 +1580,7 @@ int32_t zc_msm_run(zc_ctx *ctx, const zc_msm_generators *gens, const uint64_t *p
               pm1 + 32 * ((size_t)lo * nblk * nw1), pm0 + 32 * ((size_t)lo * nblk * 32)); nlaunch++; mark(s1, s1id, "msm_cube1_kernel");
         }
         if (seq1) {
-          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], st));
+          ZC_CUDA(ctx, cudaEventRecord(ctx->ev[2 + g], as));
           ZC_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev[2 + g], 0));
         }
         if (g == ngroups - 1)
