@@ -158,7 +158,12 @@ def cpu_secondary_rates(threads):
     t0 = time.perf_counter()
     o.msm_naive(P, s, threads=threads)
     t_msm = time.perf_counter() - t0
-    return {"point_adds_per_s": n_add / t_add, "point_add_sample": n_add,
+    n_c = 1 << 12
+    t0 = time.perf_counter()
+    o.ris_compress_batch(P[:n_sm].repeat(n_c // n_sm, axis=0), threads=threads)
+    t_c = time.perf_counter() - t0
+    return {"ristretto_compress_per_s": n_c / t_c, "ristretto_compress_sample": n_c,
+            "point_adds_per_s": n_add / t_add, "point_add_sample": n_add,
             "scalar_muls_per_s": n_sm / t_sm, "scalar_mul_sample": n_sm,
             "msm_2p20_seconds_extrapolated": t_msm * ((1 << 20) / n_sm), "msm_sample_points": n_sm,
             "note": "oracle port (1:1 restatement of edwards.rs:102-120, 465-489), linear extrapolation for the MSM"}
@@ -393,6 +398,46 @@ def run_b200(args):
             "roofline_int_fast": roofline_int((63 * 4 + 189 * 3 + 63 * 7 + 8 + 64) * 104 + 252 * 4 * 76, N_SMUL * 2 / (ms_fast * 1e-3),
                                               "4-bit signed windows: 252 dedicated doublings (4 squarings of 68 + 8 multiplies each, plus 4 products when T is "
                                               "needed -- 63 of them -- else 3) + 64 cached additions (7 products, the last 8) + the 8-entry table (64); per GPU")}
+        # ---- SURVEY.md 8f "next" rows (wire formats either side of the path, hash to group, scalar-vector ops): rates at 2^20 ---
+        n8 = 1 << 20
+        P8 = P[:n8]
+        S2 = dev_u64(synth.synth_scalar(103, 0, n8))
+        enc = torch.empty((n8, 32), dtype=torch.uint8, device=dev)
+        pts8 = torch.empty((n8, 20), dtype=torch.int64, device=dev)
+        ok8 = torch.empty(n8, dtype=torch.uint8, device=dev)
+        xy8 = torch.empty((n8, 10), dtype=torch.int64, device=dev)
+        fe8 = torch.empty((n8, 5), dtype=torch.int64, device=dev)
+        ub8 = torch.randint(0, 256, (n8, 64), dtype=torch.uint8, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        naf8 = torch.empty((n8, 256), dtype=torch.int8, device=dev)
+        f8 = {}
+
+        def rate8(tag, fn, k=3):
+            ms_, _ = timed(fn, k, 1)
+            f8[tag + "_per_s"] = n8 * world * k / (ms_ * 1e-3)
+            f8[tag + "_ms"] = ms_ / k
+        rate8("ristretto_compress", lambda: ctx.check(L.zc_ristretto_compress_batch_dev(ctx._h, P8.data_ptr(), enc.data_ptr(), n8)))
+        rate8("ristretto_decompress", lambda: ctx.check(L.zc_ristretto_decompress_batch_dev(ctx._h, enc.data_ptr(), pts8.data_ptr(), ok8.data_ptr(), n8)))
+        ctx.sync()
+        f8["decompress_all_valid"] = bool(ok8.all().item())
+        rate8("point_to_affine", lambda: ctx.check(L.zc_point_to_affine_batch_dev(ctx._h, P8.data_ptr(), xy8.data_ptr(), n8)))
+        rate8("point_is_valid", lambda: ctx.check(L.zc_point_is_valid_batch_dev(ctx._h, P8.data_ptr(), ok8.data_ptr(), n8)))
+        rate8("fe_invert", lambda: ctx.check(L.zc_fe_invert_batch_dev(ctx._h, S.data_ptr(), fe8.data_ptr(), n8)))
+        rate8("fe_pow", lambda: ctx.check(L.zc_fe_pow_batch_dev(ctx._h, S.data_ptr(), S2.data_ptr(), fe8.data_ptr(), n8)))
+        rate8("elligator", lambda: ctx.check(L.zc_ristretto_elligator_batch_dev(ctx._h, S.data_ptr(), pts8.data_ptr(), n8)))
+        rate8("from_uniform_bytes", lambda: ctx.check(L.zc_ristretto_from_uniform_bytes_batch_dev(ctx._h, ub8.data_ptr(), pts8.data_ptr(), n8)))
+        rate8("scalar_mul_mod_l", lambda: ctx.check(L.zc_scalar_mul_batch_dev(ctx._h, S.data_ptr(), S2.data_ptr(), fe8.data_ptr(), n8)), 10)
+        rate8("scalar_window_naf5", lambda: ctx.check(L.zc_scalar_window_naf_batch_dev(ctx._h, S.data_ptr(), 5, naf8.data_ptr(), n8)))
+        # integer work of the inversion: Montgomery's trick over 8 elements per thread -- 3 products per element + one a^(p-2) chain
+        # (251 dedicated squarings, popcount - 1 products) and two scaling products per 8 elements
+        e_inv = (1 << 252) + 27742317777372353535851937790883648493 - 2
+        inv_work = 3 * 104 + ((e_inv.bit_length() - 1) * 76 + (bin(e_inv).count("1") - 1 + 2) * 104) / 8.0
+        f8["roofline_int_fe_invert"] = roofline_int(inv_work, f8["fe_invert_per_s"] / world,
+                                                    "batched inversion, 8 elements per thread: 3 products (96 + 8 multiplies) per element + (251 squarings of 68 + 8 "
+                                                    "and 66 products) / 8; per GPU")
+        f8["note"] = ("SURVEY.md 8f ranks 1-4 through their _dev entry points, 2^20 elements each, outputs bit-identical to the reference "
+                      "methods (tests/test_gpu_parity.py); decompress runs on the encodings compress just produced")
+        extra["section8f_next_rows"] = f8
+        del enc, pts8, ok8, xy8, fe8, ub8, naf8, S2
         # ---- config 5: MSM, strong scaling over the N ranks (bucket-window sharding + one exchange) ----------------------
         # Three modes, same scalars: plain (arbitrary points, operand pass inside the call), prepared generators (handle,
         # Z = 1 cached operands), fixed-base tables (handle, pre-scaled rows).  At N > 1 every mode is ALSO timed on one GPU

@@ -88,29 +88,70 @@ __device__ __forceinline__ Fe mont_inv_sqrt(const Fe& v, bool& was_square) {
   return r;
 }
 
+// ---- inversion-based ops: Montgomery's trick, INV_K elements per thread -------------------------------------------------
+// The inverse is a uniquely defined value, so any way of computing it is bit-identical to the reference's Savas-Koc loop
+// (field.rs:854-925).  One a^(p-2) chain costs 251 squarings + 65 products; a thread that owns K elements multiplies them
+// together (K products), inverts the product ONCE and peels the individual inverses off again (2 K products): 3 + 318 / K
+// products per element instead of 318 -- 2^20 inversions 4.05 ms -> see profiles/.  Element j of thread t is index
+// t + j T (T = threads in the grid), so every load / store of a warp stays coalesced and a thread only ever touches its own
+// elements (in-place calls stay safe).  Zeros (inverse(0) = 0 here; the reference panics, field.rs:864) are replaced by one
+// in the product and written back as zero.
+// Representation trick: a loaded normal-form value a IS the Montgomery form of a / R, so the chain runs on the loaded words
+// directly (no to_mont per element); what comes out is R^2 / a, and the factor is taken off the running inverse once per
+// thread: SCALE = 2 Montgomery products by 1 give 1 / a (normal form), SCALE = 1 gives R / a (ready to multiply a normal-form
+// value: a x (R / b) -> a / b).
+constexpr int INV_K = 8;
+template <int SCALE, class Load, class Store>
+__device__ __forceinline__ void batch_invert(size_t n, Load&& load, Store&& store) {
+  typedef ModP M;
+  const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const Fe one = Consts<M>::R1();
+  Fe pref[INV_K];
+  Fe acc = one;
+#pragma unroll
+  for (int j = 0; j < INV_K; j++) {
+    const size_t i = t + (size_t)j * T;
+    pref[j] = acc;
+    if (i < n) {
+      const Fe x = load(i);
+      if (!fe_is_zero(x)) acc = mul_ni(acc, x);
+    }
+  }
+  Fe inv = fe_pow_const(acc, E_INV, 253);
+  const Fe unit{{1, 0, 0, 0, 0, 0, 0, 0}};
+#pragma unroll
+  for (int k = 0; k < SCALE; k++) inv = mul_ni(inv, unit);
+#pragma unroll
+  for (int j = INV_K - 1; j >= 0; j--) {
+    const size_t i = t + (size_t)j * T;
+    if (i < n) {
+      const Fe x = load(i);
+      const bool nz = !fe_is_zero(x);
+      const Fe r = mul_ni(inv, pref[j]);
+      if (nz) inv = mul_ni(inv, x);
+      store(i, nz ? r : Fe{{0, 0, 0, 0, 0, 0, 0, 0}});
+    }
+  }
+}
+inline unsigned grid_inv(size_t n) { return (unsigned)(((n + INV_K - 1) / INV_K + TPB - 1) / TPB); }
+
 __global__ void __launch_bounds__(TPB) fe_invert_kernel(const uint64_t* __restrict__ a, uint64_t* __restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  Fe x = to_mont<ModP>(fe_load52(a + 5 * i));
-  fe_store52(out + 5 * i, from_mont<ModP>(fe_pow_const(x, E_INV, 253)));
+  batch_invert<2>(n, [&](size_t i) { return fe_load52(a + 5 * i); }, [&](size_t i, const Fe& r) { fe_store52(out + 5 * i, r); });
 }
 
 // a / b = a * b^-1  (Div, field.rs:277-299; the reference asserts b != 0 -- here a / 0 = 0 like inverse(0))
 __global__ void __launch_bounds__(TPB) fe_div_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t* __restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  const Fe binv = fe_pow_const(to_mont<ModP>(fe_load52(b + 5 * i)), E_INV, 253);      // b^-1 R
-  fe_store52(out + 5 * i, mul_ni(fe_load52(a + 5 * i), binv));                          // normal * Montgomery -> normal
+  batch_invert<1>(n, [&](size_t i) { return fe_load52(b + 5 * i); },
+                  [&](size_t i, const Fe& binv) { fe_store52(out + 5 * i, mul_ni(fe_load52(a + 5 * i), binv)); });   // normal * (R / b) -> normal
 }
 
 // (x, y) = (X / Z, Y / Z)                                                                        edwards.rs:1085-1092
 __global__ void __launch_bounds__(TPB) pt_to_affine_kernel(const uint64_t* __restrict__ p, uint64_t* __restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  Fe X = fe_load52(p + 20 * i), Y = fe_load52(p + 20 * i + 5);
-  Fe zinv = fe_pow_const(to_mont<ModP>(fe_load52(p + 20 * i + 10)), E_INV, 253);   // Z^-1 R
-  fe_store52(out + 10 * i, mul_ni(X, zinv));           // normal * Montgomery -> normal
-  fe_store52(out + 10 * i + 5, mul_ni(Y, zinv));
+  batch_invert<1>(n, [&](size_t i) { return fe_load52(p + 20 * i + 10); },
+                  [&](size_t i, const Fe& zinv) {
+                    fe_store52(out + 10 * i, mul_ni(fe_load52(p + 20 * i), zinv));
+                    fe_store52(out + 10 * i + 5, mul_ni(fe_load52(p + 20 * i + 5), zinv));
+                  });
 }
 
 // Ristretto encoding                                                                             ristretto.rs:398-425
@@ -307,7 +348,7 @@ extern "C" {
 
 int32_t zc_fe_invert_batch_dev(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t n) {
   ZC_ENC_PROLOGUE(ctx, n, a && out);
-  fe_invert_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(a, out, n);
+  fe_invert_kernel<<<grid_inv(n), TPB, 0, ctx->stream>>>(a, out, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
   return ZC_OK;
@@ -321,7 +362,7 @@ int32_t zc_fe_invert_batch(zc_ctx* ctx, const uint64_t* a, uint64_t* out, size_t
 
 int32_t zc_fe_div_batch_dev(zc_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
   ZC_ENC_PROLOGUE(ctx, n, a && b && out);
-  fe_div_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(a, b, out, n);
+  fe_div_kernel<<<grid_inv(n), TPB, 0, ctx->stream>>>(a, b, out, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
   return ZC_OK;
@@ -367,7 +408,7 @@ int32_t zc_fe_sqrt_ratio_i_batch(zc_ctx* ctx, const uint64_t* u, const uint64_t*
 
 int32_t zc_point_to_affine_batch_dev(zc_ctx* ctx, const uint64_t* p, uint64_t* out_xy, size_t n) {
   ZC_ENC_PROLOGUE(ctx, n, p && out_xy);
-  pt_to_affine_kernel<<<grid_for(n), TPB, 0, ctx->stream>>>(p, out_xy, n);
+  pt_to_affine_kernel<<<grid_inv(n), TPB, 0, ctx->stream>>>(p, out_xy, n);
   ctx->launches++;
   ZC_CUDA(ctx, cudaGetLastError());
   return ZC_OK;
