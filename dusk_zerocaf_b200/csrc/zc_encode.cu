@@ -42,7 +42,7 @@ __device__ __forceinline__ Fe fe_pow_const(const Fe& a, const uint32_t* __restri
   Fe r = a;
 #pragma unroll 1
   for (int bit = nbits - 2; bit >= 0; bit--) {
-    r = sqr_ni(r);
+    r = mont_sqr<ModP>(r);                                   // inlined: ~250 of the ~315 products of a chain, no call marshalling
     if ((e[bit >> 5] >> (bit & 31)) & 1u) r = mul_ni(r, a);
   }
   return r;
