@@ -230,18 +230,19 @@ __device__ __noinline__ Fe smf_sqr(Fe a) { return mont_sqr<ModP>(a); }     // de
 // way: 36 instead of 40 products per window.  need_t is uniform over the grid (a loop counter), never a divergent branch.
 __device__ __forceinline__ Pt smf_double(const Pt& p, bool need_t) {           // pt_double_fast (dbl-2008-hwcd, a = -1)
   typedef ModP M;
-  Fe A = smf_sqr(p.X), B = smf_sqr(p.Y), Z2 = smf_sqr(p.Z);
+#ifndef ZC_SMF_INLINE
+#define ZC_SMF_INLINE 1      // measured at 2^20: 0 -> 36.93 ms, 1 -> 36.36 ms, 3 -> 38.04 ms, 4 -> 36.93 ms, 5 -> 39.20 ms (instruction cache)
+#endif
+#define ZC_SMF_SQR(X) (((ZC_SMF_INLINE >> 2) & 1) ? mont_sqr<ModP>(X) : smf_sqr(X))      // bit 2: the doubling's squarings inlined
+  Fe A = ZC_SMF_SQR(p.X), B = ZC_SMF_SQR(p.Y), Z2 = ZC_SMF_SQR(p.Z);
   Fe C = fe_add<M>(Z2, Z2);
   Fe D = fe_neg<M>(A);
   Fe S = fe_add<M>(p.X, p.Y);
-  Fe E = fe_sub<M>(fe_sub<M>(smf_sqr(S), A), B);
+  Fe E = fe_sub<M>(fe_sub<M>(ZC_SMF_SQR(S), A), B);
   Fe G = fe_add<M>(D, B);
   Fe F = fe_sub<M>(G, C);
   Fe H = fe_sub<M>(D, B);
   // ZC_SMF_INLINE bit 0: the doubling's output products inlined (no register marshalling around the calls), bit 1: the addition's
-#ifndef ZC_SMF_INLINE
-#define ZC_SMF_INLINE 1      // measured at 2^20: 0 -> 36.93 ms, 1 -> 36.40 ms, 3 -> 38.04 ms
-#endif
 #define ZC_SMF_OUT(BIT, X, Y) (((ZC_SMF_INLINE >> (BIT)) & 1) ? mont_mul<ModP>((X), (Y)) : smf_mul((X), (Y)))
   Pt r{ZC_SMF_OUT(0, E, F), ZC_SMF_OUT(0, G, H), ZC_SMF_OUT(0, F, G), p.T};
   if (need_t) r.T = ZC_SMF_OUT(0, E, H);
