@@ -90,9 +90,43 @@ __global__ void __launch_bounds__(TPB) fe_mul_square_packed_kernel(const uint8_t
 // ---- K2: point add / sub / double / neg on the ABI layout, limb-exact (edwards.rs:440-592) ----------------
 enum PtOp { PT_ADD = 0, PT_SUB = 1, PT_DOUBLE = 2, PT_NEG = 3 };
 
-// Block shape: BT threads, at least MINB resident blocks per SM (the register cap that goes with it).  The default is
-// chosen by measurement at 2^22 additions (ZC_PT_VARIANT = 0: 256 x 2, 111 registers, 0.840 ms; 1: 128 x 4, 0.835 ms;
-// 2 (default): 128 x 5, 96 registers, 0.823 ms; 3: 128 x 6, 80 registers, 0.866 ms).
+// pt_add_ref_normal (zc_point.cuh) with a selectable mix of inlined products and calls of one out-of-line multiplier:
+// ZC_PT_INLINE bit k = product k of (A, B, TT, C, D, E, F', H', X3, Y3, Z3, T3) inlined.  Twelve inlined products are ~44 KB of
+// straight-line code, more than the 32 KB instruction cache; every call costs ~16 IMAD.MOV of marshalling.
+// Measured at 2^22 additions in 128 x 4 blocks (profiles/r02_pt_add_inline_ab.txt): 0xfff (all inlined, round 1) 0.833 ms,
+// 0x000 0.770, 0xf00 0.771, 0xf03 0.756, 0xfc0 0.754, 0xfc3 0.740, 0xf0f 0.745, 0x3c0 0.753, 0xfcf 0.793, 0xfe0 0.738,
+// 0xff0 (default: the first four products through the call, eight inlined) 0.739 ms.
+#ifndef ZC_PT_INLINE
+#define ZC_PT_INLINE 0xff0
+#endif
+__device__ __noinline__ Fe pt_mul_ni(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
+#define ZC_PT_MUL(K, X, Y) (((ZC_PT_INLINE >> (K)) & 1) ? mont_mul<ModP>((X), (Y)) : pt_mul_ni((X), (Y)))
+__device__ __forceinline__ Pt pt_add_ref_normal_mix(const Pt& p, const Pt& q) {
+  typedef ModP M;
+  Fe A = ZC_PT_MUL(0, p.X, q.X);
+  Fe B = ZC_PT_MUL(1, p.Y, q.Y);
+  Fe C = ZC_PT_MUL(3, ZC_PT_MUL(2, p.T, q.T), D_MONT());
+  Fe D = ZC_PT_MUL(4, p.Z, q.Z);
+  Fe E = ZC_PT_MUL(5, fe_add<M>(p.X, p.Y), fe_add<M>(q.X, q.Y));
+  E = fe_sub<M>(fe_sub<M>(E, A), B);
+  Fe F = fe_sub<M>(D, C);
+  Fe G = fe_add<M>(D, C);
+  Fe H = fe_add<M>(B, A);
+  const Fe R4 = Consts<M>::R4();
+  F = ZC_PT_MUL(6, F, R4);
+  H = ZC_PT_MUL(7, H, R4);
+  Pt r;
+  r.X = ZC_PT_MUL(8, E, F);
+  r.Y = ZC_PT_MUL(9, G, H);
+  r.Z = ZC_PT_MUL(10, F, G);
+  r.T = ZC_PT_MUL(11, E, H);
+  return r;
+}
+#undef ZC_PT_MUL
+
+// Block shape: BT threads, at least MINB resident blocks per SM (the register cap that goes with it).  ZC_PT_VARIANT = 0: 256 x 2,
+// 1 (default): 128 x 4 -- with the mixed inlined / out-of-line products below this is the fastest (0.739 ms per 2^22 additions;
+// 128 x 5 needs 96 registers and spills around the calls: 0.81 ms), 2: 128 x 5, 3: 128 x 6.
 template <int OP, int BT, int MINB>
 __global__ void __launch_bounds__(BT, MINB) pt_op_kernel(const uint64_t* __restrict__ p, const uint64_t* __restrict__ q,
                                                          uint64_t* __restrict__ out, size_t n) {
@@ -102,12 +136,12 @@ __global__ void __launch_bounds__(BT, MINB) pt_op_kernel(const uint64_t* __restr
   Pt r;
   if (OP == PT_ADD) {
     Pt b = pt_load52(q + 20 * i);
-    r = pt_add_ref_normal(a, b);
+    r = pt_add_ref_normal_mix(a, b);
   } else if (OP == PT_SUB) {
     Pt b = pt_neg(pt_load52(q + 20 * i));   // Sub = self + (-other), edwards.rs:512
-    r = pt_add_ref_normal(a, b);
+    r = pt_add_ref_normal_mix(a, b);
   } else if (OP == PT_DOUBLE) {
-    r = pt_add_ref_normal(a, a);            // Double = self + self, edwards.rs:589-591
+    r = pt_add_ref_normal_mix(a, a);        // Double = self + self, edwards.rs:589-591
   } else {
     r = pt_neg(a);
   }
@@ -433,7 +467,7 @@ int32_t launch_pt(zc_ctx* ctx, const uint64_t* p, const uint64_t* q, uint64_t* o
     if ((rc = validation_enqueue<ModP>(ctx, p, 4 * n, 4 * ctx->vbase))) return rc;
     if (q && (rc = validation_enqueue<ModP>(ctx, q, 4 * n, 4 * ctx->vbase))) return rc;
   }
-  static const int variant = getenv("ZC_PT_VARIANT") ? atoi(getenv("ZC_PT_VARIANT")) : 2;
+  static const int variant = getenv("ZC_PT_VARIANT") ? atoi(getenv("ZC_PT_VARIANT")) : 1;
   if (variant == 1) pt_op_kernel<OP, 128, 4><<<grid_for(n, 128), 128, 0, ctx->stream>>>(p, q, out, n);
   else if (variant == 3) pt_op_kernel<OP, 128, 6><<<grid_for(n, 128), 128, 0, ctx->stream>>>(p, q, out, n);
   else if (variant != 0) pt_op_kernel<OP, 128, 5><<<grid_for(n, 128), 128, 0, ctx->stream>>>(p, q, out, n);
