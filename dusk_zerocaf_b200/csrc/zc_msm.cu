@@ -380,8 +380,10 @@ __global__ void __launch_bounds__(FINE_TPB, 2) msm_sort_fine_kernel(const uint64
   if (threadIdx.x < 256) h[threadIdx.x] = 0;
   if (fits) {
 #pragma unroll 4
-    for (uint32_t j = j0 + 2u * threadIdx.x; j < jend; j += 2u * FINE_TPB)
-      *reinterpret_cast<ulonglong2*>(fine_sm + (j - j0)) = *reinterpret_cast<const ulonglong2*>(src + j);
+    for (uint32_t j = j0 + 2u * threadIdx.x; j < jend; j += 2u * FINE_TPB) {
+      if (j + 1 < jend) *reinterpret_cast<ulonglong2*>(fine_sm + (j - j0)) = *reinterpret_cast<const ulonglong2*>(src + j);
+      else fine_sm[j - j0] = src[j];                              // the slot after the last bin's last entry was never written
+    }
   }
   __syncthreads();
   if (fits) {                                    // the histogram atomic also ranks the entry inside its bucket: kept beside the key
@@ -413,6 +415,9 @@ __global__ void __launch_bounds__(FINE_TPB, 2) msm_sort_fine_kernel(const uint64
   }
   __syncthreads();
   uint32_t* out = sorted + (size_t)prob * n_pad + start;
+  // the accumulation loads its segment's indices four at a time: the group that holds the problem's last entry reaches up to
+  // three slots past it (never used) -- make them defined
+  if (bl == (1 << pl.cb) - 1 && threadIdx.x < 4 && (size_t)start + cnt + threadIdx.x < n_pad) out[cnt + threadIdx.x] = 0u;   // stay inside this problem's array
   if (fits) {
     // bucket order is made in shared memory; the bin then leaves in one coalesced copy (scattered 4-byte stores cost a 32-byte
     // sector each at the L2: the kernel was bound by them)
@@ -585,6 +590,7 @@ __global__ void __launch_bounds__(ACC_TPB, 512 / ACC_TPB) msm_accum_kernel(const
     const uint4* src = reinterpret_cast<const uint4*>(sorted + wl * n_pad + start);
 #pragma unroll 2
     for (int j = 0; j < seg / 4; j++) {
+      if (start + 4u * j >= end) break;                         // nothing of this group is used
       uint4 v = src[j];
       idx_s[(4 * j + 0) * ACC_TPB + tx] = v.x; idx_s[(4 * j + 1) * ACC_TPB + tx] = v.y;
       idx_s[(4 * j + 2) * ACC_TPB + tx] = v.z; idx_s[(4 * j + 3) * ACC_TPB + tx] = v.w;
@@ -593,6 +599,7 @@ __global__ void __launch_bounds__(ACC_TPB, 512 / ACC_TPB) msm_accum_kernel(const
     const uint2* src = reinterpret_cast<const uint2*>(sorted + wl * n_pad + start);
 #pragma unroll 2
     for (int j = 0; j < seg / 2; j++) {
+      if (start + 2u * j >= end) break;
       uint2 v = src[j];
       idx_s[(2 * j + 0) * ACC_TPB + tx] = v.x; idx_s[(2 * j + 1) * ACC_TPB + tx] = v.y;
     }
@@ -979,7 +986,9 @@ __global__ void __launch_bounds__(128) msm_stitch_quad_kernel(BucketSrc src, uin
 #pragma unroll 1
   for (int k = 1; k <= mx; k++) {
     const bool on = k <= np;
-    const Fe r = quad_add(acc, ld_pt(H + 32 * (size_t)(on ? s_first + k : 0)), q, qbase);
+    Pt nxt = pt_identity_mont();                                    // quads that are done add the identity (and keep acc): no load of a slot nobody wrote
+    if (on) nxt = ld_pt(H + 32 * (size_t)(s_first + k));
+    const Fe r = quad_add(acc, nxt, q, qbase);
     if (on) acc = r;
   }
   if (write) st_coord(buckets + 32 * g, q, fe_canon4(acc));          // canonical: load_bucket / msm_fold_kernel read these too
