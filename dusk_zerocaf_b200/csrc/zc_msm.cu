@@ -94,23 +94,55 @@ __global__ void __launch_bounds__(PREP_TPB) msm_prep_kernel(const uint64_t* __re
 // prepared points: normalise to Z = 1 first (one inversion per point, paid once per point set), so that every later
 // accumulation step is a 7-multiplication mixed addition.  Cached form (y+x, y-x, 1, 2dxy), all in Montgomery form.
 __device__ __noinline__ Fe prep_mul(Fe a, Fe b) { return mont_mul<ModP>(a, b); }
-__global__ void __launch_bounds__(128) msm_prep_affine_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
-  typedef ModP M;
-  size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
-  if (i >= n) return;
-  Pt p = pt_to_mont(pt_load52(points + 20 * i));
-  // Z^(p-2): p - 2 = 2^252 + (c - 2), plain square-and-multiply over a compile-time exponent
-  const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
-  Fe zi = p.Z;
+// z^(p-2), Montgomery form (one chain per THREAD: the per-point inverses come from Montgomery's trick below)
+__device__ __forceinline__ Fe prep_invert(const Fe& z) {
+  const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};   // p - 2
+  Fe zi = z;
 #pragma unroll 1
   for (int bit = 251; bit >= 0; bit--) {
     zi = mont_sqr<ModP>(zi);
-    if ((e[bit >> 5] >> (bit & 31)) & 1u) zi = prep_mul(zi, p.Z);
+    if ((e[bit >> 5] >> (bit & 31)) & 1u) zi = prep_mul(zi, z);
   }
-  const Fe x = prep_mul(p.X, zi), y = prep_mul(p.Y, zi);
-  uint32_t* o = cached + 32 * i;
+  return zi;
+}
+// affine cached form (y+x, y-x, 1, 2dxy) of a point given X, Y and 1/Z (all Montgomery form)
+__device__ __forceinline__ void prep_store_affine(uint32_t* __restrict__ o, const Fe& X, const Fe& Y, const Fe& zi) {
+  typedef ModP M;
+  const Fe x = prep_mul(X, zi), y = prep_mul(Y, zi);
   st_fe(o, fe_add<M>(y, x)); st_fe(o + 8, fe_sub<M>(y, x)); st_fe(o + 16, Consts<M>::R1());
   st_fe(o + 24, prep_mul(prep_mul(x, y), D2_MONT()));
+}
+// A thread owns PREP_K points (index t + j T, coalesced): the Z's are multiplied together, the product is inverted ONCE
+// (~320 products) and the individual inverses are peeled off (3 products per point) -- one inversion per point before.
+// The loaded normal-form Z is used as it is (the Montgomery form of Z / R): the peeled value is R^2 / Z, one product by 1 on
+// the running inverse (once per thread) turns it into R / Z, i.e. 1 / Z in Montgomery form for the X R, Y R of to_mont.
+// Z = 0 (not a point) is treated as 1 so that it cannot poison its neighbours; its own entry is then garbage, as before.
+constexpr int PREP_K = 8;
+__global__ void __launch_bounds__(128) msm_prep_affine_kernel(const uint64_t* __restrict__ points, uint32_t* __restrict__ cached, size_t n) {
+  typedef ModP M;
+  const size_t T = (size_t)gridDim.x * 128, t = (size_t)blockIdx.x * 128 + threadIdx.x;
+  Fe pref[PREP_K];
+  Fe acc = Consts<M>::R1();
+#pragma unroll
+  for (int j = 0; j < PREP_K; j++) {
+    const size_t i = t + (size_t)j * T;
+    pref[j] = acc;
+    if (i < n) {
+      const Fe z = fe_load52(points + 20 * i + 10);
+      if (!fe_is_zero(z)) acc = prep_mul(acc, z);
+    }
+  }
+  Fe inv = prep_mul(prep_invert(acc), Fe{{1, 0, 0, 0, 0, 0, 0, 0}});
+#pragma unroll
+  for (int j = PREP_K - 1; j >= 0; j--) {
+    const size_t i = t + (size_t)j * T;
+    if (i < n) {
+      const Fe z = fe_load52(points + 20 * i + 10);
+      const Fe zi = prep_mul(inv, pref[j]);                          // R / Z_i: Montgomery form of 1 / Z_i
+      if (!fe_is_zero(z)) inv = prep_mul(inv, z);
+      prep_store_affine(cached + 32 * i, to_mont<M>(fe_load52(points + 20 * i)), to_mont<M>(fe_load52(points + 20 * i + 5)), zi);
+    }
+  }
 }
 
 // ---- digits + histogram ----------------------------------------------------------------------------------------
@@ -164,24 +196,30 @@ __global__ void __launch_bounds__(128) msm_fixed_base_table_kernel(const uint64_
   size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
   if (i >= n) return;
   Pt p = pt_to_mont(pt_load52(points + 20 * i));
-  const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
+  // Pass 1: walk up the windows; at every owned window park the UNNORMALISED (X, Y, Z) in the row itself, with the product of
+  // the Z's before it in the row's fourth slot.  Pass 2: one inversion of the whole product, then Montgomery's trick backwards
+  // over the rows -- 7 products per row + one chain per point instead of a chain per row (16 rows per point on one GPU).
   int at = 0;                                    // p = 2^at P_i
+  Fe acc = Consts<M>::R1();
 #pragma unroll 1
   for (int t = 0; t < win.nwl; t++) {
     const int target = c * (int)win.w[t] - merged_spread_bits(c, (int)win.w[t]);
 #pragma unroll 1
     for (int j = at; j < target; j++) p = prep_double(p);
     at = target;
-    Fe zi = p.Z;
-#pragma unroll 1
-    for (int bit = 251; bit >= 0; bit--) {
-      zi = mont_sqr<ModP>(zi);
-      if ((e[bit >> 5] >> (bit & 31)) & 1u) zi = prep_mul(zi, p.Z);
-    }
-    const Fe x = prep_mul(p.X, zi), y = prep_mul(p.Y, zi);
     uint32_t* o = table + 32 * ((size_t)t * n + i);
-    st_fe(o, fe_add<M>(y, x)); st_fe(o + 8, fe_sub<M>(y, x)); st_fe(o + 16, Consts<M>::R1());
-    st_fe(o + 24, prep_mul(prep_mul(x, y), D2_MONT()));
+    st_fe(o, p.X); st_fe(o + 8, p.Y); st_fe(o + 16, p.Z); st_fe(o + 24, acc);
+    if (!fe_is_zero(p.Z)) acc = prep_mul(acc, p.Z);
+  }
+  Fe inv = prep_invert(acc);
+#pragma unroll 1
+  for (int t = win.nwl - 1; t >= 0; t--) {
+    uint32_t* o = table + 32 * ((size_t)t * n + i);
+    Fe X, Y, Z, pre;
+    ld_fe(o, X); ld_fe(o + 8, Y); ld_fe(o + 16, Z); ld_fe(o + 24, pre);
+    const Fe zi = prep_mul(inv, pre);
+    if (!fe_is_zero(Z)) inv = prep_mul(inv, Z);
+    prep_store_affine(o, X, Y, zi);
   }
 }
 
@@ -1740,7 +1778,7 @@ int32_t zc_msm_generators_create_dev(zc_ctx *ctx, const uint64_t *points, size_t
   if (kind == ZC_GEN_PREPARED) {
     // normalise to Z = 1 once (one inversion per point): every later bucket addition is a 7-multiplication mixed addition
     ZC_GEN_CUDA(cudaMalloc(&g->cached, n * 128));
-    msm_prep_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)g->cached, n);
+    msm_prep_affine_kernel<<<(unsigned)(((n + PREP_K - 1) / PREP_K + 127) / 128), 128, 0, ctx->stream>>>(points, (uint32_t*)g->cached, n);
     ctx->launches++;
     ZC_GEN_CUDA(cudaGetLastError());
   } else {
